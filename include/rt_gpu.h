@@ -1,0 +1,205 @@
+/*
+ * rt_gpu.h — C ABI of the B200 path-tracing backend.
+ *
+ * This is the drop-in boundary for the per-pixel Monte-Carlo integrator of
+ * firelion9/raytracing-course-hw-public.  The reference has no FFI of its own;
+ * the seam is the single call `run_raytracer(scene, img)` at
+ * src/main.cpp:37 (definition src/raytracer.h:629-674).  A host that keeps the
+ * reference's loader (src/scene.h:183), BVH build (src/bvh.h:368) and image
+ * writer (src/image.h:34) replaces that one call by
+ *
+ *     rt_gpu_create -> rt_gpu_upload_scene -> rt_gpu_render -> rt_gpu_readback
+ *
+ * and then feeds the float means to Image::set_pixel (src/image.h:40), so the
+ * tonemap / gamma / PPM path stays the reference's own code.
+ *
+ * Conventions: plain C, POD structs, caller-owned host pointers that are only
+ * read during the call (everything is copied to the device), int return codes
+ * (0 = ok, negative = rt_status), no exceptions cross the boundary, one caller
+ * thread per handle.  There is no CPU fallback: every entry point fails with
+ * RT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef RT_GPU_H
+#define RT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_GPU_ABI_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID_ARG = -1,
+    RT_ERR_NO_DEVICE = -2,  /* no CUDA device / driver: there is no CPU path */
+    RT_ERR_CUDA = -3,       /* a CUDA runtime call failed; see rt_gpu_last_error */
+    RT_ERR_NO_SCENE = -4,   /* render/readback before upload */
+    RT_ERR_NO_RENDER = -5,  /* readback before render */
+    RT_ERR_NCCL = -6,       /* multi-device reduce failed / NCCL not loadable */
+    RT_ERR_BAD_SCENE = -7,  /* inconsistent rt_scene_desc (ids out of range ...) */
+    RT_ERR_OOM = -8
+} rt_status;
+
+#define RT_NO_CHILD 0xFFFFFFFFu /* mirrors NO_CHILD, src/bvh.h:154 */
+
+/* Mirror of `BVHNode` (src/bvh.h:157-163): 40 bytes, same field order, so a
+ * reference host can pass `bvh.nodes.data()` without conversion.  A node is
+ * either inner (two children, obj_begin == obj_end) or a leaf (no children,
+ * objects [obj_begin, obj_end) of the BVH's object order). */
+typedef struct rt_bvh_node {
+    float bmin[3];
+    float bmax[3];
+    uint32_t left_child;
+    uint32_t right_child;
+    uint32_t obj_begin;
+    uint32_t obj_end;
+} rt_bvh_node;
+
+/* One BVH in the reference's representation (src/bvh.h:165-168).  `objects`
+ * replaces the `const Object*` vector by indices into scene.objects order. */
+typedef struct rt_bvh_desc {
+    uint32_t n_nodes;
+    uint32_t root;          /* RT_NO_CHILD when the BVH is empty */
+    uint32_t n_objects;
+    uint32_t _pad;
+    const rt_bvh_node *nodes;
+    const uint32_t *objects; /* n_objects ids into the triangle arrays */
+} rt_bvh_desc;
+
+/* Mirror of `geometry::material` (src/geometry.h:604-614) with the Texture
+ * pointers replaced by indices; -1 selects the built-in 1x1 default
+ * (WHITE_TEXTURE, or NORMAL_UP for normal_tex; src/geometry.h:601-602). */
+typedef struct rt_material {
+    float color[4];
+    float emission[3];
+    float roughness;
+    float metallic;
+    float ior;
+    int32_t color_tex;
+    int32_t emissive_tex;
+    int32_t metallic_roughness_tex;
+    int32_t normal_tex;
+} rt_material;
+
+/* Texture = RGBA8 texels, row-major, `offset` bytes into `texels`.  The
+ * reference keeps float4 texels that are exactly u8/255 (src/geometry.h:592-595)
+ * so 8-bit storage loses nothing. */
+typedef struct rt_texture {
+    uint32_t width;
+    uint32_t height;
+    uint64_t offset;
+} rt_texture;
+
+/* Camera (src/scene.h:60-72) without width/height, which are render params. */
+typedef struct rt_camera {
+    float position[3];
+    float right[3];
+    float up[3];
+    float forward[3];
+    float fov_x;
+} rt_camera;
+
+/* The flattened scene a host builds from the reference structures
+ * (Scene src/scene.h:74-90, RaytracerStaticContext src/raytracer.h:434-455). */
+typedef struct rt_scene_desc {
+    uint32_t abi_version;     /* RT_GPU_ABI_VERSION */
+    uint32_t n_tris;          /* scene.objects.size() */
+    rt_camera camera;
+    float bg_color[3];        /* Scene::bg_color, constant sky (src/main.cpp:28) */
+    /* compile-time knobs of src/config.h, passed as data */
+    float eps;                /* EPS = 1e-4, config.h:15 */
+    float min_roughness;      /* MIN_ROUGHNESS = 0.04, config.h:20 */
+    float vndf_factor;        /* VNDF_factor = 1/3, config.h:26 */
+    uint32_t ray_depth;       /* Scene::ray_depth = DEFAULT_RAY_DEPTH = 8 */
+    uint32_t n_materials;
+    uint32_t n_textures;
+    uint32_t _pad0;
+    uint64_t texel_bytes;
+    /* per-triangle arrays in scene.objects order (Object, geometry.h:639-659) */
+    const float *tri_pos;          /* n_tris*9: a,b,c            */
+    const float *tri_normals;      /* n_tris*9: per-vertex normals */
+    const float *tri_uv;           /* n_tris*6: per-vertex uv    */
+    const float *tri_tangents;     /* n_tris*9 or NULL => (1,0,0) */
+    const uint32_t *tri_material;  /* n_tris ids into materials  */
+    const rt_material *materials;
+    const rt_texture *textures;
+    const uint8_t *texels;
+    rt_bvh_desc scene_bvh;         /* over all triangles (raytracer.h:441-443) */
+    rt_bvh_desc light_bvh;         /* over emission != 0 (raytracer.h:444-447) */
+} rt_scene_desc;
+
+typedef enum rt_render_mode {
+    RT_MODE_BEAUTY = 0,      /* jittered Monte-Carlo estimate (render_pixel, raytracer.h:618) */
+    RT_MODE_PRIMARY_IDS = 1  /* pixel-centre rays (gen_ray, raytracer.h:516) -> closest triangle id */
+} rt_render_mode;
+
+typedef struct rt_render_params {
+    uint32_t width;
+    uint32_t height;
+    uint32_t samples;        /* total spp of the image */
+    uint32_t sample_begin;   /* this call renders samples [sample_begin, sample_end) of every pixel */
+    uint32_t sample_end;     /* 0 => samples */
+    uint32_t mode;           /* rt_render_mode */
+    uint64_t seed;           /* Philox key */
+    uint32_t max_paths_in_flight; /* 0 => default (8 Mi) */
+    uint32_t flags;          /* RT_FLAG_* */
+} rt_render_params;
+
+#define RT_FLAG_ACCUMULATE 1u /* add to the existing sums instead of clearing them */
+
+/* Work counters of the last render (all devices summed). */
+typedef struct rt_stats {
+    uint64_t samples;          /* pixel-samples traced */
+    uint64_t extension_rays;   /* closest-hit traversals (cast_ray, raytracer.h:540) */
+    uint64_t light_pdf_rays;   /* all-hit light-BVH traversals (bvh_mix_dist::pdf, raytracer.h:363) */
+    uint64_t shades;           /* shade() evaluations incl. alpha pass-throughs */
+    double render_ms;          /* device time of rt_gpu_render (CUDA events), max over devices */
+    double reduce_ms;          /* device time of the multi-device reduce (0 for one device) */
+    double kernel_ms[8];       /* per-kernel device time: 0 generate 1 extend 2 shade 3 accumulate 4 ids; filled only with RT_PROFILE_KERNELS */
+    uint64_t kernel_launches;  /* kernels launched by the last rt_gpu_render */
+} rt_stats;
+
+typedef struct rt_gpu_ctx rt_gpu_ctx;
+
+/* n_gpus devices starting at first_device (single-process multi-device: one
+ * stream per device, ncclReduce to device 0).  Use n_gpus = 1 and the rank's
+ * own device when the caller runs one process per GPU. */
+int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device);
+void rt_gpu_destroy(rt_gpu_ctx *ctx);
+
+int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene);
+
+/* Asynchronous with respect to the host only inside the call: returns after
+ * the device work (and, for n_gpus > 1, the reduce to device 0) completed. */
+int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params);
+
+/* rgb_mean: width*height*3 floats = per-pixel sum / samples (the argument of
+ * Image::set_pixel, image.h:40); prim_ids: width*height int32 (scene.objects
+ * index of the primary hit, -1 on miss; only after RT_MODE_PRIMARY_IDS).
+ * Either pointer may be NULL. */
+int rt_gpu_readback(rt_gpu_ctx *ctx, float *rgb_mean, int32_t *prim_ids, rt_stats *stats);
+
+/* Device pointer of device 0's per-pixel float sums (width*height*4 floats,
+ * rgb + unused w) so that a one-process-per-GPU caller can hand it to its own
+ * collective (e.g. torch.distributed.reduce over NCCL) before readback. */
+int rt_gpu_accum_device_ptr(rt_gpu_ctx *ctx, void **dptr, size_t *n_floats);
+
+/* Device-side tonemap + quantise of the current sums (image.h:49-82):
+ * rgb8 = width*height*3 bytes, ready to follow the "P6" header. */
+int rt_gpu_readback_rgb8(rt_gpu_ctx *ctx, uint8_t *rgb8);
+
+/* Per-kernel timing (serialises launches with events; off by default). */
+int rt_gpu_set_profiling(rt_gpu_ctx *ctx, int enable);
+
+const char *rt_gpu_last_error(void);
+int rt_gpu_device_count(void);
+int rt_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RT_GPU_H */
