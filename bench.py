@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py — Msamples/s of the path-tracing hot path on B200 (BASELINE.json metric).
+
+Workload (config 4 of BASELINE.json): the synthetic "Sponza-scale" glTF of SURVEY.md 8(d) — 260 192 triangles,
+textured, 32 emissive triangles — at 1000 x 1000 pixels, 1000 spp per GPU.  One step = one full render
+(1e9 pixel-samples per GPU).  With N GPUs (one process per GPU, torchrun) rank r renders samples
+[1000 r, 1000 (r+1)) of every pixel, i.e. a 1000 N spp image ("weak" scaling), followed by the path's single
+collective: one NCCL reduce(sum) of the W*H*4 float accumulation buffer to rank 0, inside the timed region.
+
+  value        device-timed (CUDA events) samples/s of K steps, scene resident in HBM
+  e2e          the same through the public C ABI with host buffers every step: rt_gpu_upload_scene (host
+               re-pack + H2D of the whole scene) -> rt_gpu_render -> rt_gpu_readback (D2H of the float means)
+  roofline     dominant kernel k_extend (BVH traversal) against the measured FP32 FMA rate; algorithmic
+               flops = 24/box test + 70/triangle test of the REFERENCE's traversal, counted by
+               the oracle on a sample of the same workload
+  cpu_baseline the unmodified reference (oracle/_ref, kind "reference") or the oracle port, timed on this box's
+               host cores on a bounded sample of the same scene
+
+`--impl reference` times the reference's own CPU implementation instead (same metric / config keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "scenes")]
+
+SCENE = "big_lights"
+WIDTH = HEIGHT = 1000
+SPP_PER_GPU = 1000
+METRIC = "Msamples/s"
+FLOP_BOX, FLOP_TRI = 24.0, 70.0  # slab test, Cramer triangle test
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def scene_path(name):
+    """Deterministic synthetic scene, generated on first use (one private copy per rank: no write races)."""
+    import gen_gltf
+
+    d = os.path.join(ROOT, "scenes", "cache", "rank" + os.environ.get("RANK", "0"))
+    p = os.path.join(d, name + ".gltf")
+    if not os.path.exists(p):
+        gen_gltf.generate(name, d)
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_throughput(budget_s, width=500, height=500):
+    """Msamples/s of the reference CPU path on `SCENE`: wall(run_raytracer, spp_hi) - wall(spp = 1), which
+    cancels the two BVH builds inside run_raytracer (raytracer.h:633); all hardware threads
+    (raytracer.h:636).  Falls back to the oracle port when oracle/_ref was not built."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib as O
+
+    cores = os.cpu_count() or 1
+    gltf = scene_path(SCENE)
+    if O.have_ref_tool():
+        def wall(spp):
+            r = subprocess.run([O.REF_TOOL, "time", gltf, str(width), str(height), str(spp)], capture_output=True,
+                               text=True, check=True)
+            return float(r.stderr.strip().splitlines()[-1])
+
+        t1 = wall(1)
+        t5 = wall(5)
+        rate = width * height * 4 / max(t5 - t1, 1e-3)  # samples/s pilot
+        spp_hi = int(max(8, min(4096, 1 + budget_s * rate / (width * height))))
+        thi = wall(spp_hi)
+        v = width * height * (spp_hi - 1) / max(thi - t1, 1e-6) / 1e6
+        return {"value": v, "unit": METRIC, "cores": cores, "kind": "reference",
+                "sample": f"{SCENE} {width}x{height}, run_raytracer wall(spp={spp_hi}) - wall(spp=1) = "
+                          f"{thi - t1:.2f} s, unmodified reference (oracle/_ref/ref_tool time)"}
+    import rt_b200
+    from rt_b200 import gltf as gl
+
+    scene = gl.load_gltf(gltf, width / height)
+    t0 = time.perf_counter()
+    O.render(scene, width, height, 1, rng_mode=O.RNG_MINSTD, n_threads=cores)
+    rate = width * height / (time.perf_counter() - t0)
+    spp = int(max(2, min(4096, budget_s * rate / (width * height))))
+    t0 = time.perf_counter()
+    O.render(scene, width, height, spp, rng_mode=O.RNG_MINSTD, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": width * height * spp / dt / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": f"{SCENE} {width}x{height} x {spp} spp in {dt:.2f} s, oracle/pt_oracle.c (minstd mode)"}
+
+
+def reference_counts():
+    """Per-extension-ray work of the REFERENCE's traversal on this workload (oracle counters)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib as O
+    from rt_b200 import gltf as gl
+
+    scene = gl.load_gltf(scene_path(SCENE), WIDTH / HEIGHT)
+    _, st = O.render(scene, 100, 100, 4, rng_mode=O.RNG_PHILOX, seed=1)
+    e = max(st["extension_rays"], 1)
+    return {"box_tests_per_ray": st["box_tests"] / e, "tri_tests_per_ray": st["tri_tests"] / e,
+            "nodes_per_ray": st["nodes_visited"] / e, "rays_per_sample": e / st["samples"],
+            "light_box_per_lray": st["light_box_tests"] / max(st["light_pdf_rays"], 1),
+            "light_tri_per_lray": st["light_tri_tests"] / max(st["light_pdf_rays"], 1)}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    # each step is a bounded sample sized so that the whole run ends within a few minutes
+    per_step = max(2.0, min(20.0, 150.0 / max(steps + warm, 1)))
+    vals = []
+    for i in range(warm + steps):
+        r = cpu_throughput(per_step, 250, 250)
+        if i >= warm:
+            vals.append(r)
+    v = sum(x["value"] for x in vals) / len(vals)
+    samples_per_step = WIDTH * HEIGHT * SPP_PER_GPU
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": samples_per_step / (v * 1e6) * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": v / 0.355, "dtype": "f32", "data": "synthetic",
+           "config": config_dict(args.gpus, extra={"note": "CPU arm: each step is a bounded sample (250x250) of the "
+                                                           "workload; ms_per_step is the extrapolated full step"}),
+           "cpu_baseline": {**vals[-1], "value": v},
+           "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(n_gpus, extra=None):
+    c = {"workload": f"BASELINE config 4: synthetic Sponza-scale glTF '{SCENE}' (260192 triangles, textured, 32 "
+                     f"emissive), {WIDTH}x{HEIGHT}, {SPP_PER_GPU} spp per GPU, ray depth 8",
+         "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP_PER_GPU, "spp_total": SPP_PER_GPU * n_gpus,
+         "parallelism": f"sample-split x{n_gpus} + 1 NCCL reduce" if n_gpus > 1 else "single GPU",
+         "l2": "256 MiB written between steps; per-step path-queue traffic (>100 GB) far exceeds the 126 MB L2"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import rt_b200  # noqa: F401
+    from rt_b200 import dist as rtdist
+    from rt_b200 import gltf as gl
+    from rt_b200 import gpu
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this backend has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w, h, spp_gpu = args.width, args.height, args.spp
+    spp_total = spp_gpu * world
+    t0 = time.perf_counter()
+    scene = gl.load_gltf(scene_path(args.scene), w / h)
+    t_load = time.perf_counter() - t0
+    rt = gpu.RtGpu(1, local_rank)
+    t0 = time.perf_counter()
+    rt.upload_scene(scene)
+    t_upload = time.perf_counter() - t0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    seed = 20261018
+
+    def step(i):
+        flush.fill_(i & 255)  # L2 flush between iterations
+        sums = rtdist.render_distributed(rt, w, h, spp_total, seed, rank, world, local_rank)
+        return sums
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    rays = [0, 0]
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+        st = rt.stats()
+        launches += st["kernel_launches"] + (1 if world > 1 else 0)
+        rays[0] += st["extension_rays"]
+        rays[1] += st["light_pdf_rays"]
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    ray_t = torch.tensor(rays, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ray_t, op=dist.ReduceOp.SUM)
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = float(ms.item())
+    samples_all = float(w) * h * spp_total * args.steps
+    value = samples_all / (total_ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers every step through the C ABI ------------------------------------------------
+    host_out = np.empty((h, w, 3), np.float32)
+    scene_bytes = sum(a.nbytes for a in scene._sections() if a is not None)
+
+    def e2e_step():
+        rt.upload_scene(scene)  # host re-pack + H2D of the whole scene
+        sums = rtdist.render_distributed(rt, w, h, spp_total, seed, rank, world, local_rank)
+        if rank == 0:
+            rt.readback_into(host_out)  # D2H of the per-pixel sums, / spp on the host
+        return sums
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = samples_all / float(e2e_s.item()) / 1e6
+
+    # ---- roofline of the dominant kernel + CPU baseline (rank 0 only) ---------------------------------
+    roof = cpu = counts = None
+    kernel_ms = None
+    if rank == 0:
+        rt.set_profiling(True)
+        sb, se = rtdist.sample_range(spp_total, rank, world)
+        rt.render(w, h, spp_total, seed=seed, sample_begin=sb, sample_end=se)
+        pst = rt.stats()
+        rt.set_profiling(False)
+        kernel_ms = {"generate": pst["kernel_ms"][0], "extend": pst["kernel_ms"][1], "shade": pst["kernel_ms"][2],
+                     "accumulate": pst["kernel_ms"][3], "render_total": pst["render_ms"]}
+        peak = rt.fp32_peak_tflops()
+        counts = reference_counts()
+        flop_per_ray = FLOP_BOX * counts["box_tests_per_ray"] + FLOP_TRI * counts["tri_tests_per_ray"]
+        n_ext_launches = max(1, (pst["kernel_launches"] // (2 + 2 * scene.ray_depth)) * scene.ray_depth)
+        achieved = flop_per_ray * pst["extension_rays"] / (pst["kernel_ms"][1] * 1e-3) / 1e12
+        roof = {"bound": "fp32", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": "measured on this GPU by rt_gpu_fp32_peak (FFMA loop); MEASURED_PEAKS.json has no FP32 "
+                               "entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                "algorithmic_flop_per_ray": flop_per_ray, "rays_per_launch": pst["extension_rays"] / n_ext_launches,
+                "avg_launch_ms": pst["kernel_ms"][1] / n_ext_launches, "launches": n_ext_launches,
+                "extend_share_of_step": pst["kernel_ms"][1] / max(pst["render_ms"], 1e-9),
+                "mrays_per_s_in_kernel": pst["extension_rays"] / (pst["kernel_ms"][1] * 1e-3) / 1e6}
+        if world == 1:
+            cpu = cpu_throughput(args.cpu_budget)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": value / 0.355, "dtype": "f32", "data": "synthetic",
+               "config": config_dict(world, {"scene": args.scene, "width": w, "height": h, "spp_per_gpu": spp_gpu,
+                                             "spp_total": spp_total}),
+               "mrays_per_s": {"extension": float(ray_t[0].item()) / (total_ms * 1e-3) / 1e6,
+                               "light_pdf": float(ray_t[1].item()) / (total_ms * 1e-3) / 1e6},
+               "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(scene_bytes),
+                       "d2h_bytes_per_step": int(w * h * 16)},
+               "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+               "kernel_ms_profiled_step": kernel_ms, "reference_work_per_ray": counts,
+               "host_s": {"load_and_bvh_build": t_load, "first_upload": t_upload},
+               "vs_baseline_note": "0.355 Msamples/s = README.md:4 (Sponza 1000x1000x1000spp in ~47 min, unknown CPU)"}
+        print(json.dumps(out), flush=True)
+    barrier()
+    rt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default=SCENE)
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--spp", type=int, default=SPP_PER_GPU, help="samples per pixel per GPU")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    libs = [os.path.join(ROOT, "raytracing-course-hw-public_b200", n) for n in ("librt_gpu.so", "librt_host.so")]
+    libs.append(os.path.join(ROOT, "oracle", "libpt_oracle.so"))
+    if not all(os.path.exists(p) for p in libs):
+        if rank == 0:
+            import __graft_entry__ as entry
+
+            entry.build()
+        else:
+            while not all(os.path.exists(p) for p in libs):
+                time.sleep(0.5)
+            time.sleep(2.0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    run_gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -194,6 +194,10 @@ int rt_gpu_readback_rgb8(rt_gpu_ctx *ctx, uint8_t *rgb8);
 /* Per-kernel timing (serialises launches with events; off by default). */
 int rt_gpu_set_profiling(rt_gpu_ctx *ctx, int enable);
 
+/* Diagnostic: measured FP32 FMA rate of device 0 in TFLOP/s (dependent-chain-free FFMA loop on every
+ * SM) — the denominator of the FP32 roofline the traversal / shading kernels are reported against. */
+int rt_gpu_fp32_peak(rt_gpu_ctx *ctx, double *tflops);
+
 const char *rt_gpu_last_error(void);
 int rt_gpu_device_count(void);
 int rt_gpu_abi_version(void);

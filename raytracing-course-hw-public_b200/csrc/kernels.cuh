@@ -1,0 +1,233 @@
+// kernels.cuh — the wavefront kernels (sm_100a).  One "batch" = npix pixels x k samples = N paths:
+//
+//   k_generate   N paths: Philox pixel jitter -> camera ray (gen_ray, raytracer.h:527-538)
+//   for bounce b in [0, ray_depth):
+//     k_extend   closest-hit BVH traversal of queue b (cast_ray -> BVH::intersect_ray, bvh.h:170-235)
+//     k_shade    hit data + shade() state transition (raytracer.h:555-591), light pdf traversal,
+//                survivors compacted into queue b+1 with warp-aggregated (__ballot/__popc) appends
+//   k_accumulate per-sample NaN scrub + per-pixel float sums (render_pixel, raytracer.h:607-627)
+//
+// Path state is SoA of float4 (128-bit coalesced loads/stores), ping-ponged between queue b and b+1:
+//   q_o   = (origin.xyz,     pixel index bits)
+//   q_d   = (direction.xyz,  sample index bits)
+//   q_thr = (throughput.rgb, unused)
+//   hit   = (t, beta, gamma, BVH-order triangle index bits or -1)      written by extend, read by shade
+//   rad   = per-path radiance accumulator, indexed by the path's fixed slot (no atomics: one owner)
+// extend and shade are persistent: grid = SMs x resident CTAs, each warp pulls 32 queue entries at a
+// time from a device counter, so no host round trip is needed to size a launch.
+#ifndef RT_KERNELS_CUH
+#define RT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+
+#include "pt_core.cuh"
+#include "rt_types.h"
+
+namespace rt {
+
+struct BatchParams {
+    uint32_t pix0;      // first pixel (row-major index) of this batch
+    uint32_t npix;      // pixels in this batch
+    uint32_t s0;        // first sample index of this batch
+    uint32_t k;         // samples per pixel in this batch
+    uint32_t width, height;
+    uint32_t k0, k1;    // Philox key
+};
+
+struct Queues {
+    float4 *o[2], *d[2], *thr[2];
+    float4 *hit;
+    float4 *rad;
+    uint32_t *count;        // [ray_depth + 1] queue sizes
+    uint32_t *fetch_ext;    // [ray_depth] work-fetch cursors of k_extend
+    uint32_t *fetch_shade;  // [ray_depth] work-fetch cursors of k_shade
+    unsigned long long *stats;  // [4] extension rays, light pdf rays, shades, samples
+};
+
+constexpr int kExtendThreads = 128;
+constexpr int kShadeThreads = 128;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// warp pulls the next 32 queue entries; returns the index of this lane's entry (may be >= count)
+__device__ __forceinline__ uint32_t warp_fetch(uint32_t *cursor) {
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(cursor, 32u);
+    return __shfl_sync(0xFFFFFFFFu, base, 0) + lane_id();
+}
+
+// warp-aggregated append: one atomicAdd per warp, slots handed out by __popc of the lower lanes
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool active) {
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, active);
+    uint32_t base = 0;
+    if (lane_id() == 0 && mask) base = atomicAdd(counter, static_cast<uint32_t>(__popc(mask)));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + static_cast<uint32_t>(__popc(mask & ((1u << lane_id()) - 1u)));
+}
+
+__global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Queues q) {
+    const uint32_t n = bp.npix * bp.k;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) {
+        q.count[0] = n;
+        atomicAdd(q.stats + 3, static_cast<unsigned long long>(n));
+    }
+    if (slot >= n) return;
+    const uint32_t j = slot / bp.npix;
+    const uint32_t pl = slot - j * bp.npix;
+    const uint32_t pixel = bp.pix0 + pl;
+    const uint32_t sample = bp.s0 + j;
+    const uint32_t py = pixel / bp.width, px = pixel - py * bp.width;
+    const RngKey key{pixel, sample, bp.k0, bp.k1};
+    const u4 r = rng_jitter(key);
+    const f3 dir = camera_dir(cam, static_cast<float>(px) + u01(r.x), static_cast<float>(py) + u01(r.y));
+    q.o[0][slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel));
+    q.d[0][slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample));
+    q.thr[0][slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, Queues q, uint32_t bounce) {
+    const uint32_t count = q.count[bounce];
+    const float4 *__restrict__ qo = q.o[bounce & 1];
+    const float4 *__restrict__ qd = q.d[bounce & 1];
+    for (;;) {
+        const uint32_t i = warp_fetch(q.fetch_ext + bounce);
+        if (i - lane_id() >= count) break;
+        if (i < count) {
+            const float4 o = qo[i], d = qd[i];
+            const Hit h = closest_hit(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), eps);
+            q.hit[i] = make_float4(h.t, h.b, h.c, __int_as_float(h.tri));
+        }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(q.stats + 0, static_cast<unsigned long long>(count));
+}
+
+__global__ void __launch_bounds__(kShadeThreads) k_shade(DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q,
+                                                        uint32_t bounce) {
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
+    __syncthreads();
+    const uint32_t count = q.count[bounce];
+    const int in = bounce & 1, out = in ^ 1;
+    const bool last = bounce + 1 == s.ray_depth;
+    uint32_t n_light = 0, n_shade = 0;
+    for (;;) {
+        const uint32_t i = warp_fetch(q.fetch_shade + bounce);
+        if (i - lane_id() >= count) break;
+        bool alive = false;
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(0, 0, 0);
+        uint32_t pixel = 0, sample = 0;
+        if (i < count) {
+            const float4 o4 = q.o[in][i], d4 = q.d[in][i], t4 = q.thr[in][i], h4 = q.hit[i];
+            o = mk3(o4.x, o4.y, o4.z);
+            d = mk3(d4.x, d4.y, d4.z);
+            thr = mk3(t4.x, t4.y, t4.z);
+            pixel = __float_as_uint(o4.w);
+            sample = __float_as_uint(d4.w);
+            Hit h;
+            h.t = h4.x;
+            h.b = h4.y;
+            h.c = h4.z;
+            h.tri = __float_as_int(h4.w);
+            const RngKey key{pixel, sample, bp.k0, bp.k1};
+            f3 rad = mk3(0, 0, 0);
+            n_shade += h.tri >= 0 ? 1u : 0u;
+            alive = shade_bounce(s, lut, key, bounce, last, h, o, d, thr, rad, n_light);
+            if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f) {  // NaN != 0 is true: poisons the sample like the reference
+                const uint32_t slot = (sample - bp.s0) * bp.npix + (pixel - bp.pix0);
+                float4 acc = q.rad[slot];
+                acc.x += rad.x;
+                acc.y += rad.y;
+                acc.z += rad.z;
+                q.rad[slot] = acc;
+            }
+        }
+        const uint32_t dst = warp_append(q.count + bounce + 1, alive);
+        if (alive) {
+            q.o[out][dst] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
+            q.d[out][dst] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
+            q.thr[out][dst] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+        }
+    }
+    // block-level reduction of the work counters -> one atomic per CTA
+    __shared__ uint32_t s_cnt[2];
+    if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
+    __syncthreads();
+    for (int off = 16; off > 0; off >>= 1) {
+        n_light += __shfl_down_sync(0xFFFFFFFFu, n_light, off);
+        n_shade += __shfl_down_sync(0xFFFFFFFFu, n_shade, off);
+    }
+    if (lane_id() == 0) {
+        atomicAdd(&s_cnt[0], n_light);
+        atomicAdd(&s_cnt[1], n_shade);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_cnt[0]) atomicAdd(q.stats + 1, static_cast<unsigned long long>(s_cnt[0]));
+        if (s_cnt[1]) atomicAdd(q.stats + 2, static_cast<unsigned long long>(s_cnt[1]));
+    }
+}
+
+// accum[pixel] += sum_j sanitize(rad[j * npix + p])  — fixed order, deterministic, no atomics
+__global__ void __launch_bounds__(256) k_accumulate(BatchParams bp, const float4 *__restrict__ rad, float4 *__restrict__ accum) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= bp.npix) return;
+    f3 sum = mk3(0, 0, 0);
+    for (uint32_t j = 0; j < bp.k; ++j) {
+        const float4 v = rad[static_cast<size_t>(j) * bp.npix + p];
+        sum = sum + sanitize(mk3(v.x, v.y, v.z));
+    }
+    float4 a = accum[bp.pix0 + p];
+    a.x += sum.x;
+    a.y += sum.y;
+    a.z += sum.z;
+    accum[bp.pix0 + p] = a;
+}
+
+// RT_MODE_PRIMARY_IDS: pixel-centre rays (gen_ray(camera, x, y), raytracer.h:516-525) -> scene.objects id
+__global__ void __launch_bounds__(128) k_primary_ids(Camera cam, DBvh bvh, float eps, uint32_t width, uint32_t height,
+                                                     int32_t *__restrict__ ids) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= width * height) return;
+    const uint32_t y = p / width, x = p - y * width;
+    const f3 dir = camera_dir(cam, static_cast<float>(x) + 0.5f, static_cast<float>(y) + 0.5f);
+    const Hit h = closest_hit(bvh, cam.pos, dir, eps);
+    ids[p] = h.tri < 0 ? -1 : static_cast<int32_t>(bvh.tris[h.tri].id_last & ~RT_LAST_BIT);
+}
+
+// Device-side Image::set_pixel (image.h:40-82): mean -> ACES -> gamma 1/2.2 -> x255 -> clamp -> round
+__global__ void __launch_bounds__(256) k_tonemap(const float4 *__restrict__ accum, float samples, uint32_t n_pixels,
+                                                 uint8_t *__restrict__ rgb8) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    const float4 a = accum[p];
+    const float c[3] = {a.x / samples, a.y / samples, a.z / samples};  // `res / samples`, raytracer.h:626
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = c[k];
+        const float m = (x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f);
+        const float v = powf(m, 1.0f / 2.2f) * 255.0f;
+        const float cl = fminf(fmaxf(v, 0.0f), 255.0f);  // NaN -> 0
+        rgb8[static_cast<size_t>(p) * 3 + k] = static_cast<uint8_t>(roundf(cl));
+    }
+}
+
+// FP32 roofline probe: 16 independent FFMA chains per thread, no memory traffic.
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, float a, float b, int iters) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = static_cast<float>(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace rt
+
+#endif  // RT_KERNELS_CUH

@@ -1,0 +1,589 @@
+// pt_core.cuh — per-ray / per-bounce device math of the wavefront path tracer.
+//
+// Everything here is a pure function of its arguments and is marked RT_HD so that the same source
+// can also be compiled by the host compiler for unit tests of the math (tests/hostcheck); the
+// kernels in kernels.cu only add the queue plumbing.  Each function cites the reference code whose
+// semantics it has to keep (Appendix B of SURVEY.md lists why each detail matters).
+#ifndef RT_PT_CORE_CUH
+#define RT_PT_CORE_CUH
+
+#include <math.h>
+#include <stdint.h>
+
+#include "rt_types.h"
+
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#define RT_D __device__ __forceinline__
+#else
+#define RT_HD inline
+#define RT_D inline
+#endif
+
+namespace rt {
+
+// ------------------------------------------------------------------------------------------------
+// small vector types
+// ------------------------------------------------------------------------------------------------
+struct f3 {
+    float x, y, z;
+};
+struct alignas(16) f4 {
+    float x, y, z, w;
+};
+
+RT_HD f3 mk3(float x, float y, float z) { return f3{x, y, z}; }
+RT_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_HD f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+RT_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RT_HD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_HD float len2(f3 a) { return dot(a, a); }
+RT_HD f3 normalize(f3 a) { return a * (1.0f / sqrtf(len2(a))); }  // geometry::norm, geometry.h:31-34
+RT_HD bool any_nan(f3 a) { return (a.x != a.x) || (a.y != a.y) || (a.z != a.z); }
+
+#define RT_PI 3.14159265358979323846f
+#define RT_INV_PI 0.31830988618379067154f
+
+// 128-bit read-only loads (L1/L2 resident scene data)
+#if defined(__CUDA_ARCH__)
+RT_HD f4 ld4(const void *p) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    return f4{v.x, v.y, v.z, v.w};
+}
+RT_HD uint32_t ldu(const uint32_t *p) { return __ldg(p); }
+#else
+RT_HD f4 ld4(const void *p) { return *reinterpret_cast<const f4 *>(p); }
+RT_HD uint32_t ldu(const uint32_t *p) { return *p; }
+#endif
+
+RT_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+RT_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 keyed (pixel, sample, 2*bounce + block); replaces std::minstd_rand seeded per span
+// (raytracer.h:456-489, 646-648).  Lane assignment per bounce (<= 6 uniforms):
+//   block 0: [0] alpha coin  [1] strategy coin  [2] vndf u1 | mixture selector  [3] vndf u2 | light index
+//   block 1: [0],[1] cosine (z, phi) | light point (u, v)
+//   counter word 2 = 0xFFFFFFFF: [0],[1] pixel jitter
+// ------------------------------------------------------------------------------------------------
+RT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
+}
+
+struct u4 {
+    uint32_t x, y, z, w;
+};
+
+RT_HD u4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return u4{c0, c1, c2, c3};
+}
+RT_HD float u01(uint32_t bits) { return static_cast<float>(bits >> 8) * (1.0f / 16777216.0f); }  // [0,1)
+
+struct RngKey {
+    uint32_t pixel, sample, k0, k1;
+};
+RT_HD u4 rng_block(const RngKey &k, uint32_t bounce, uint32_t block) {
+    return philox4x32_10(k.pixel, k.sample, 2u * bounce + block, 0u, k.k0, k.k1);
+}
+RT_HD u4 rng_jitter(const RngKey &k) { return philox4x32_10(k.pixel, k.sample, 0xFFFFFFFFu, 0u, k.k0, k.k1); }
+
+// ------------------------------------------------------------------------------------------------
+// camera: gen_ray, raytracer.h:516-538; fov_y from Camera::fov_y, scene.h:69-71 (host-computed tans)
+// ------------------------------------------------------------------------------------------------
+struct Camera {
+    f3 pos, right, up, fwd;
+    float tan_half_x, tan_half_y;
+    float inv_w2, inv_h2;  // 2/width, 2/height
+};
+
+RT_HD f3 camera_dir(const Camera &c, float px, float py) {
+    const float a = (px * c.inv_w2 - 1.0f) * c.tan_half_x;
+    const float b = (py * c.inv_h2 - 1.0f) * c.tan_half_y;
+    return normalize(a * c.right - b * c.up + c.fwd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// intersection primitives (src/bvh.h)
+// ------------------------------------------------------------------------------------------------
+struct Hit {
+    float t, b, c;  // distance and the barycentrics of vertex b and c (xs.z, xs.x, xs.y of bvh.h:45-47)
+    int32_t tri;    // BVH-order triangle index, -1 = miss
+};
+
+// intersect(ray, aabb, min_dst), bvh.h:137-152 with the division replaced by a multiplication with
+// 1/dir.  Returns the entry distance max(t_min, min_dst) or a negative value on a miss.
+RT_HD float slab(float lox, float loy, float loz, float hix, float hiy, float hiz, f3 o, f3 idir, float min_dst) {
+    const float x0 = (lox - o.x) * idir.x, x1 = (hix - o.x) * idir.x;
+    const float y0 = (loy - o.y) * idir.y, y1 = (hiy - o.y) * idir.y;
+    const float z0 = (loz - o.z) * idir.z, z1 = (hiz - o.z) * idir.z;
+    const float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+    const float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return (tmin <= tmax && tmax >= min_dst) ? fmaxf(tmin, min_dst) : -1.0f;
+}
+
+// intersect_ray_triangle + intersect(ray, triangle, min_dst), bvh.h:36-65 (Cramer's rule written as
+// scalar triple products).  Accept iff beta >= 0, gamma >= 0, beta + gamma <= 1, t >= min_dst.
+RT_HD bool tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float min_dst, float &t, float &beta, float &gamma) {
+    const f3 n = cross(e1, e2);
+    const float det = -dot(d, n);
+    const f3 y = o - a;
+    const f3 r = cross(d, y);
+    const float inv = 1.0f / det;
+    beta = -dot(e2, r) * inv;
+    gamma = dot(e1, r) * inv;
+    t = dot(y, n) * inv;
+    return beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= min_dst;
+}
+
+struct TravCounters {
+    uint32_t nodes, tris;
+};
+
+// BVH::intersect_ray, bvh.h:170-235, iteratively: near child first (ties: left first, bvh.h:216),
+// far child visited only while the best hit is farther than its entry distance (bvh.h:221),
+// strictly-closer-wins / first-found-wins-ties (bvh.h:132).
+RT_HD Hit closest_hit(const DBvh &bvh, f3 o, f3 d, float min_dst) {
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0.0f;
+    best.tri = -1;
+    if (bvh.root == RT_LINK_NONE) return best;
+    const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int32_t stack_link[RT_STACK_SIZE];
+    float stack_t[RT_STACK_SIZE];
+    int sp = 0;
+    int32_t link = bvh.root;
+    for (;;) {
+        if (link >= 0) {
+            const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
+            const f4 n0 = ld4(p), n1 = ld4(p + 16), n2 = ld4(p + 32), n3 = ld4(p + 48);
+            const float dl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, idir, min_dst);
+            const float dr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, idir, min_dst);
+            const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
+            const bool hl = dl >= 0.0f && dl < best.t, hr = dr >= 0.0f && dr < best.t;
+            if (hl && hr) {
+                const bool swap = dl > dr;
+                stack_link[sp] = swap ? ll : lr;
+                stack_t[sp] = swap ? dl : dr;
+                ++sp;
+                link = swap ? lr : ll;
+                continue;
+            }
+            if (hl || hr) {
+                link = hl ? ll : lr;
+                continue;
+            }
+        } else {
+            uint32_t k = static_cast<uint32_t>(~link);
+            for (;;) {
+                const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+                const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+                float t, b, c;
+                if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, min_dst, t, b,
+                             c) &&
+                    t < best.t) {
+                    best.t = t;
+                    best.b = b;
+                    best.c = c;
+                    best.tri = static_cast<int32_t>(k);
+                }
+                if (f2u(t0.w) & RT_LAST_BIT) break;
+                ++k;
+            }
+        }
+        // pop, skipping subtrees that can no longer contain a closer hit
+        for (;;) {
+            if (sp == 0) return best;
+            --sp;
+            if (stack_t[sp] < best.t) {
+                link = stack_link[sp];
+                break;
+            }
+        }
+    }
+}
+
+// bvh_mix_dist::pdf, raytracer.h:363-375: ALL hits along (x, dir) with t >= eps, occluded or not,
+// both faces; each contributes |y - x|^2 / (|dir . n_y| * area) (raytracer.h:79-84,255-261);
+// the sum is divided by the number of lights.  BVH::foreach_intersection, bvh.h:237-260.
+RT_HD float light_pdf(const DScene &s, f3 x, f3 dir) {
+    const DBvh &bvh = s.light;
+    if (bvh.root == RT_LINK_NONE) return 0.0f;
+    const f3 idir = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    int32_t stack_link[RT_STACK_SIZE];
+    int sp = 0;
+    int32_t link = bvh.root;
+    float sum = 0.0f;
+    for (;;) {
+        if (link >= 0) {
+            const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
+            const f4 n0 = ld4(p), n1 = ld4(p + 16), n2 = ld4(p + 32), n3 = ld4(p + 48);
+            const bool hl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, x, idir, s.eps) >= 0.0f;
+            const bool hr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, x, idir, s.eps) >= 0.0f;
+            const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
+            if (hl && hr) {
+                stack_link[sp++] = lr;
+                link = ll;
+                continue;
+            }
+            if (hl || hr) {
+                link = hl ? ll : lr;
+                continue;
+            }
+        } else {
+            uint32_t k = static_cast<uint32_t>(~link);
+            for (;;) {
+                const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+                const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+                float t, b, c;
+                if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), x, dir, s.eps, t, b,
+                             c)) {
+                    const f4 le = ld4(s.light_extra + k);
+                    // y = x + dir*t; |x - y|^2 and norm(y - x) as the reference forms them
+                    const f3 y = x + dir * t;
+                    const f3 xy = y - x;
+                    const float d2 = len2(xy);
+                    const f3 w = xy * (1.0f / sqrtf(d2));
+                    sum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);
+                }
+                if (f2u(t0.w) & RT_LAST_BIT) break;
+                ++k;
+            }
+        }
+        if (sp == 0) break;
+        link = stack_link[--sp];
+    }
+    return sum / static_cast<float>(s.n_lights);
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures + materials (src/geometry.h:517-631) and hit shading data (to_intersection_info, bvh.h:80-121)
+// ------------------------------------------------------------------------------------------------
+// Texture::sample: repeat wrap, texel = (int)(u*W) without half-texel offset, bilinear with wrapped
+// neighbours, per-texel gamma BEFORE interpolation (LUT == powf(k/255, 2.2f)), alpha untouched;
+// 1-texel textures are returned raw (geometry.h:548-550).
+RT_HD f4 tex_sample(const DScene &s, const float *lut, int32_t tex, float u, float v, bool gamma) {
+    const f4 ti = ld4(s.textures + tex);
+    const uint32_t off = f2u(ti.x), w = f2u(ti.y), h = f2u(ti.z);
+    const float k255 = 1.0f / 255.0f;
+    if (w * h == 1u) {
+        const uint32_t p = ldu(s.texels + off);
+        return f4{(p & 255u) * k255, ((p >> 8) & 255u) * k255, ((p >> 16) & 255u) * k255, (p >> 24) * k255};
+    }
+    const float tx = (u - floorf(u)) * static_cast<float>(w);
+    const float ty = (v - floorf(v)) * static_cast<float>(h);
+    uint32_t x0 = static_cast<uint32_t>(static_cast<int>(tx)), y0 = static_cast<uint32_t>(static_cast<int>(ty));
+    x0 = x0 < w ? x0 : w - 1;  // u - floor(u) can round to 1.0f
+    y0 = y0 < h ? y0 : h - 1;
+    const float dx = tx - static_cast<float>(x0), dy = ty - static_cast<float>(y0);
+    const uint32_t x1 = (x0 == w - 1) ? 0u : x0 + 1, y1 = (y0 == h - 1) ? 0u : y0 + 1;  // mod_inc, geometry.h:521
+    const uint32_t p00 = ldu(s.texels + off + x0 + y0 * w), p01 = ldu(s.texels + off + x0 + y1 * w);
+    const uint32_t p10 = ldu(s.texels + off + x1 + y0 * w), p11 = ldu(s.texels + off + x1 + y1 * w);
+    const float wx0 = 1.0f - dx, wy0 = 1.0f - dy;
+    f4 r;
+    if (gamma) {
+#define RT_BIL(sh) (wx0 * (wy0 * lut[(p00 >> sh) & 255u] + dy * lut[(p01 >> sh) & 255u]) + \
+                    dx * (wy0 * lut[(p10 >> sh) & 255u] + dy * lut[(p11 >> sh) & 255u]))
+        r.x = RT_BIL(0);
+        r.y = RT_BIL(8);
+        r.z = RT_BIL(16);
+#undef RT_BIL
+    } else {
+#define RT_BIL(sh) (wx0 * (wy0 * (((p00 >> sh) & 255u) * k255) + dy * (((p01 >> sh) & 255u) * k255)) + \
+                    dx * (wy0 * (((p10 >> sh) & 255u) * k255) + dy * (((p11 >> sh) & 255u) * k255)))
+        r.x = RT_BIL(0);
+        r.y = RT_BIL(8);
+        r.z = RT_BIL(16);
+#undef RT_BIL
+    }
+    r.w = wx0 * (wy0 * ((p00 >> 24) * k255) + dy * ((p01 >> 24) * k255)) +
+          dx * (wy0 * ((p10 >> 24) * k255) + dy * ((p11 >> 24) * k255));
+    return r;
+}
+
+// ray_intersection_info, bvh.h:18-29 (normals already flipped towards the ray, bvh.h:111-112)
+struct Surface {
+    f3 ng, ns;     // geometric / shading normal
+    f3 color;      // base colour rgb
+    float alpha;   // base colour alpha (coverage)
+    f3 emission;
+    float metallic, roughness, ior;
+};
+
+RT_HD Surface make_surface(const DScene &s, const float *lut, const Hit &h, f3 dir) {
+    Surface sf;
+    const char *tp = reinterpret_cast<const char *>(s.scene.tris + h.tri);
+    const f4 t1 = ld4(tp + 16), t2 = ld4(tp + 32);
+    const char *ap = reinterpret_cast<const char *>(s.attrs + h.tri);
+    const f4 a0 = ld4(ap), a1 = ld4(ap + 16), a2 = ld4(ap + 32), a3 = ld4(ap + 48);
+    f3 ng = normalize(cross(mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z)));  // Object::base_normal
+    const bool inside = dot(ng, dir) > 0.0f;                                   // bvh.h:92
+    const float w0 = 1.0f - h.b - h.c;                                         // triangle::interop, geometry.h:497-502
+    f3 smooth = normalize(mk3(a0.x, a0.y, a0.z) * w0 + mk3(a1.x, a1.y, a1.z) * h.b + mk3(a2.x, a2.y, a2.z) * h.c);
+    if (dot(ng, smooth) < 0.0f) smooth = -smooth;  // bvh.h:95-97
+    const float tu = a0.w * w0 + a2.w * h.b + a3.y * h.c;
+    const float tv = a1.w * w0 + a3.x * h.b + a3.z * h.c;
+    const char *mp = reinterpret_cast<const char *>(s.materials + f2u(a3.w));
+    const f4 m0 = ld4(mp), m1 = ld4(mp + 16), m2 = ld4(mp + 32), m3 = ld4(mp + 48);
+    const int32_t color_tex = static_cast<int32_t>(f2u(m2.z)), emissive_tex = static_cast<int32_t>(f2u(m2.w));
+    const int32_t mr_tex = static_cast<int32_t>(f2u(m3.x)), normal_tex = static_cast<int32_t>(f2u(m3.y));
+
+    f3 ns = smooth;
+    if (normal_tex >= 0) {  // default NORMAL_UP decodes to (0,0,1): shading normal = smooth normal
+        f3 tangent = mk3(1.0f, 0.0f, 0.0f);
+        if (s.tangents) {
+            const char *gp = reinterpret_cast<const char *>(s.tangents + h.tri);
+            const f4 g0 = ld4(gp), g1 = ld4(gp + 16), g2 = ld4(gp + 32);
+            tangent = normalize(mk3(g0.x, g0.y, g0.z) * w0 + mk3(g0.w, g1.x, g1.y) * h.b + mk3(g1.z, g1.w, g2.x) * h.c);
+        }
+        const f3 bitangent = cross(smooth, tangent);  // not normalised, bvh.h:102
+        const f4 n01 = tex_sample(s, lut, normal_tex, tu, tv, false);
+        const f3 nl = normalize(mk3(n01.x * 2.0f - 1.0f, n01.y * 2.0f - 1.0f, n01.z * 2.0f - 1.0f));
+        ns = normalize(nl.x * tangent + nl.y * bitangent + nl.z * smooth);
+    } else if (s.tangents) {
+        // (0,0,1) in a frame whose z is `smooth`: still the smooth normal
+        ns = smooth;
+    }
+    sf.ng = inside ? -ng : ng;
+    sf.ns = inside ? -ns : ns;
+
+    f4 col = f4{m0.x, m0.y, m0.z, m0.w};
+    if (color_tex >= 0) {
+        const f4 c = tex_sample(s, lut, color_tex, tu, tv, true);
+        col = f4{col.x * c.x, col.y * c.y, col.z * c.z, col.w * c.w};
+    }
+    sf.color = mk3(col.x, col.y, col.z);
+    sf.alpha = col.w;
+    sf.emission = mk3(m1.x, m1.y, m1.z);
+    if (emissive_tex >= 0) {
+        const f4 e = tex_sample(s, lut, emissive_tex, tu, tv, true);
+        sf.emission = sf.emission * mk3(e.x, e.y, e.z);
+    }
+    sf.roughness = m1.w;
+    sf.metallic = m2.x;
+    if (mr_tex >= 0) {
+        const f4 mr = tex_sample(s, lut, mr_tex, tu, tv, false);
+        sf.metallic *= mr.z;   // metallic = B, roughness = G (geometry.h:623-626)
+        sf.roughness *= mr.y;
+    }
+    sf.ior = m2.y;
+    return sf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling distributions (src/raytracer.h:86-262) and BRDF (raytracer.h:264-343)
+// ------------------------------------------------------------------------------------------------
+RT_HD void sincos_2pi(float u, float &s, float &c) {  // sin/cos(2*pi*u)
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * u, &s, &c);
+#else
+    s = sinf(2.0f * RT_PI * u);
+    c = cosf(2.0f * RT_PI * u);
+#endif
+}
+
+RT_HD f3 choose_local_x(f3 n) {  // VNDF_dist::choose_local_x, raytracer.h:208-219
+    f3 r = mk3(1.0f, 1.0f, 1.0f);
+    const float dn = n.x + n.y + n.z;
+    if (fabsf(n.x) > 0.5f) r.x -= dn / n.x;
+    else if (fabsf(n.y) > 0.5f) r.y -= dn / n.y;
+    else r.z -= dn / n.z;
+    return normalize(r);
+}
+
+// VNDF_dist::sample (Heitz 2018), raytracer.h:140-173. alpha = max(roughness, MIN_ROUGHNESS)^2.
+RT_HD f3 vndf_sample(float alpha, f3 in_dir, f3 ns, float u1, float u2) {
+    const f3 nx = choose_local_x(ns);
+    const f3 ny = cross(ns, nx);
+    const f3 v = -normalize(mk3(dot(nx, in_dir), dot(ny, in_dir), dot(ns, in_dir)));
+    const f3 vh = normalize(mk3(alpha * v.x, alpha * v.y, v.z));
+    const float lensq = vh.x * vh.x + vh.y * vh.y;
+    const f3 T1 = lensq > 0.0f ? mk3(-vh.y, vh.x, 0.0f) * (1.0f / sqrtf(lensq)) : mk3(1.0f, 0.0f, 0.0f);
+    const f3 T2 = cross(vh, T1);
+    const float r = sqrtf(u1);
+    float sp, cp;
+    sincos_2pi(u2, sp, cp);
+    const float t1 = r * cp;
+    float t2 = r * sp;
+    const float sh = 0.5f * (1.0f + vh.z);
+    t2 = (1.0f - sh) * sqrtf(1.0f - t1 * t1) + sh * t2;
+    const float t3 = sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+    const f3 nh = t1 * T1 + t2 * T2 + t3 * vh;
+    const f3 ne = normalize(mk3(alpha * nh.x, alpha * nh.y, fmaxf(0.0f, nh.z)));
+    const f3 res_n = normalize(ne.x * nx + ne.y * ny + ne.z * ns);
+    return in_dir - res_n * (2.0f * dot(in_dir, res_n));  // geometry::reflect
+}
+
+// VNDF_dist::pdf, raytracer.h:175-206
+RT_HD float vndf_pdf(float alpha, float eps, f3 in_dir, f3 ns, f3 dir) {
+    const f3 nx = choose_local_x(ns);
+    const f3 ny = cross(ns, nx);
+    const f3 v = -mk3(dot(nx, in_dir), dot(ny, in_dir), dot(ns, in_dir));
+    const f3 hw = normalize(dir - in_dir);
+    const f3 n = mk3(dot(nx, hw), dot(ny, hw), dot(ns, hw));
+    const float vdn = dot(v, n);
+    if (!(vdn > 0.0f)) return 0.0f;
+    const float ax = v.x * alpha, ay = v.y * alpha;
+    const float lambda = (-1.0f + sqrtf(1.0f + (ax * ax + ay * ay) / (v.z * v.z))) * 0.5f;
+    const float g1 = 1.0f / (1.0f + lambda);
+    const float nxa = n.x / alpha, nya = n.y / alpha;
+    const float q = nxa * nxa + nya * nya + n.z * n.z;
+    const float dn = RT_INV_PI / (alpha * alpha * q * q);
+    // g1 * vdn * dn / max(eps, v.z) / 4 / vdn
+    return g1 * vdn * dn / fmaxf(eps, v.z) * 0.25f / vdn;
+}
+
+// cosine_dist::sample = norm(n + uniform_sphere), sphere from z in U[-1,1], phi in U[0,2pi) (raytracer.h:94-121)
+RT_HD f3 cosine_sample(f3 ng, float u1, float u2) {
+    const float z = u1 * 2.0f - 1.0f;
+    const float cz = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float sp, cp;
+    sincos_2pi(u2, sp, cp);
+    return normalize(ng + mk3(cz * cp, cz * sp, z));
+}
+RT_HD float cosine_pdf(f3 ng, f3 dir) { return fmaxf(dot(ng, dir) * RT_INV_PI, 0.0f); }  // raytracer.h:123-128
+
+// bvh_mix_dist::sample -> triangle_dist::sample, raytracer.h:227-239,355-361: uniform light index,
+// (u,v) folded, p = A + (B-A)*v + (C-A)*u.
+RT_HD f3 light_sample(const DScene &s, f3 x, float u_index, float u, float v) {
+    uint32_t k = static_cast<uint32_t>(u_index * static_cast<float>(s.n_lights));
+    k = k < s.n_lights ? k : s.n_lights - 1;
+    const char *p = reinterpret_cast<const char *>(s.light.tris + k);
+    const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+    if (u + v > 1.0f) {
+        u = 1.0f - u;
+        v = 1.0f - v;
+    }
+    const f3 pt = mk3(t0.x, t0.y, t0.z) + mk3(t1.x, t1.y, t1.z) * v + mk3(t2.x, t2.y, t2.z) * u;
+    return normalize(pt - x);
+}
+
+RT_HD float pow5(float x) {
+    const float x2 = x * x;
+    return x * x2 * x2;
+}
+
+// specular_brdf = V * D, raytracer.h:273-293
+RT_HD float specular_brdf(float alpha, f3 in_dir, f3 out_dir, f3 ns, f3 h) {
+    const float a2 = alpha * alpha;
+    const float ndh = dot(ns, h);
+    const float dd = ndh * ndh * (a2 - 1.0f) + 1.0f;
+    const float d = (ndh > 0.0f ? a2 : 0.0f) * RT_INV_PI / (dd * dd);
+    const float ndo = dot(ns, out_dir), ndi = -dot(ns, in_dir);
+    const float div1 = fabsf(ndo) + sqrtf(a2 + (1.0f - a2) * ndo * ndo);
+    const float div2 = fabsf(ndi) + sqrtf(a2 + (1.0f - a2) * ndi * ndi);
+    const float vis = (dot(h, out_dir) > 0.0f && -dot(h, in_dir) > 0.0f) ? 1.0f / (div1 * div2) : 0.0f;
+    return vis * d;
+}
+
+// pbr_brdf, raytracer.h:295-343: (1-m) * mix(diffuse c/pi, spec, F(ior)) + m * spec * (c + (1-c) F5)
+RT_HD f3 pbr_brdf(const Surface &sf, float alpha, f3 in_dir, f3 out_dir) {
+    const f3 h = normalize(out_dir - in_dir);  // halfway, raytracer.h:131-134
+    const float spec = specular_brdf(alpha, in_dir, out_dir, sf.ns, h);
+    const float p5 = pow5(1.0f - fabsf(dot(-in_dir, h)));
+    f3 res = mk3(0.0f, 0.0f, 0.0f);
+    if (sf.metallic < 1.0f) {
+        const float r0 = (1.0f - sf.ior) / (1.0f + sf.ior);
+        const float f0 = r0 * r0;
+        const float fr = f0 + (1.0f - f0) * p5;
+        const f3 diel = sf.color * (RT_INV_PI * (1.0f - fr)) + mk3(spec, spec, spec) * fr;
+        res = res + (1.0f - sf.metallic) * diel;
+    }
+    if (sf.metallic > 0.0f) {
+        const f3 f = mk3(sf.color.x + (1.0f - sf.color.x) * p5, sf.color.y + (1.0f - sf.color.y) * p5,
+                         sf.color.z + (1.0f - sf.color.z) * p5);
+        res = res + sf.metallic * (spec * f);
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one bounce of shade(), raytracer.h:555-591, as a state transition of an iterative path:
+//   radiance += throughput * (what this hit returns when the recursion below it is 0)
+//   throughput *= scl  (raytracer.h:580-590)
+// Returns true when the path continues with (o, d).
+// ------------------------------------------------------------------------------------------------
+RT_HD bool shade_bounce(const DScene &s, const float *lut, const RngKey &key, uint32_t bounce, bool last_bounce,
+                        const Hit &h, f3 &o, f3 &d, f3 &thr, f3 &radiance, uint32_t &light_rays) {
+    if (h.tri < 0) {  // miss: Scene::bg_at with the constant white environment, scene.h:83-89
+        radiance = radiance + thr * mk3(s.bg[0], s.bg[1], s.bg[2]);
+        return false;
+    }
+    const Surface sf = make_surface(s, lut, h, d);
+    const f3 pos = o + d * h.t;  // ray.at(t): the next ray starts exactly here, no normal offset
+    const u4 r0 = rng_block(key, bounce, 0);
+    if (!(u01(r0.x) <= sf.alpha)) {  // alpha pass-through consumes a bounce, drops this hit's emission (raytracer.h:559-561)
+        o = pos;
+        return !last_bounce;
+    }
+    radiance = radiance + thr * sf.emission;  // every remaining exit of shade() returns emission (+ ...)
+    if (last_bounce) return false;            // trace_ray(depth 0) = 0, raytracer.h:596-598
+    const float rough = fmaxf(sf.roughness, s.min_roughness);
+    const float alpha = rough * rough;
+    f3 dir;
+    if (u01(r0.y) <= s.vndf_factor) {
+        dir = vndf_sample(alpha, d, sf.ns, u01(r0.z), u01(r0.w));
+    } else {
+        const u4 r1 = rng_block(key, bounce, 1);
+        // mix_dist{cosine, bvh_mix}: uniform selector, raytracer.h:383-392; cosine only without lights (:449-453)
+        const bool pick_light = s.n_lights > 0 && !(u01(r0.z) * 2.0f < 1.0f);
+        dir = pick_light ? light_sample(s, pos, u01(r0.w), u01(r1.x), u01(r1.y)) : cosine_sample(sf.ng, u01(r1.x), u01(r1.y));
+    }
+    if (any_nan(dir)) return false;  // raytracer.h:569-571
+    const float p_vndf = vndf_pdf(alpha, s.eps, d, sf.ns, dir);
+    float p_mis = cosine_pdf(sf.ng, dir);
+    if (s.n_lights > 0) {  // mix_dist::pdf = mean of the sub-pdfs, raytracer.h:395-407
+        p_mis = (p_mis + light_pdf(s, pos, dir)) * 0.5f;
+        ++light_rays;
+    }
+    const float p = s.vndf_factor * p_vndf + (1.0f - s.vndf_factor) * p_mis;
+    if (p < s.eps) return false;  // raytracer.h:576-578 (NaN p continues, like the reference)
+    const f3 scl = pbr_brdf(sf, alpha, d, dir) * (fmaxf(0.0f, dot(dir, sf.ns)) / p);
+    if (len2(scl) == 0.0f) return false;  // raytracer.h:584-586
+    thr = thr * scl;
+    o = pos;
+    d = dir;
+    return true;
+}
+
+// sanitize_nans, raytracer.h:607-616: per channel NaN -> 0, Inf kept
+RT_HD f3 sanitize(f3 c) { return mk3(c.x != c.x ? 0.0f : c.x, c.y != c.y ? 0.0f : c.y, c.z != c.z ? 0.0f : c.z); }
+
+}  // namespace rt
+
+#endif  // RT_PT_CORE_CUH

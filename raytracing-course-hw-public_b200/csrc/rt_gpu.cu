@@ -1,0 +1,567 @@
+// rt_gpu.cu — implementation of the C ABI in include/rt_gpu.h on top of the wavefront kernels.
+//
+// One DeviceState per GPU (own stream, own copy of the scene, own queues).  A render splits the
+// sample range across the devices of the handle (sample-split), every device runs
+// its batches asynchronously on its stream, and for more than one device the per-pixel float sums
+// are merged with a single ncclReduce(sum) to device 0.  NCCL is resolved with dlopen at the first
+// multi-device create so that single-device users never need the library.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "repack.h"
+#include "rt_gpu.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_CHECK(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(_e == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA,                          \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                                 \
+    } while (0)
+
+// ---- minimal NCCL binding (dlopen) ---------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (handle) return true;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) return false;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(handle, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        Reduce = reinterpret_cast<decltype(Reduce)>(dlsym(handle, "ncclReduce"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(handle, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(handle, "ncclGroupEnd"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        return CommInitAll && CommDestroy && Reduce && GroupStart && GroupEnd;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat32 = 7;  // ncclFloat32
+constexpr int kNcclSum = 0;      // ncclSum
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return RT_OK;
+        release();
+        if (count == 0) return RT_OK;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(RT_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        n = count;
+        return RT_OK;
+    }
+    int upload(const std::vector<T> &v, cudaStream_t s) {
+        if (int rc = alloc(std::max<size_t>(v.size(), 1))) return rc;
+        if (!v.empty()) CU_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+        return RT_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+enum KernelKind { K_GENERATE = 0, K_EXTEND = 1, K_SHADE = 2, K_ACCUMULATE = 3, K_IDS = 4, K_COUNT = 8 };
+
+struct DeviceState {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
+    // scene
+    DevBuf<DNode> nodes, lnodes;
+    DevBuf<DTri> tris, ltris;
+    DevBuf<DAttr> attrs;
+    DevBuf<DTangent> tangents;
+    DevBuf<DLight> light_extra;
+    DevBuf<DMat> materials;
+    DevBuf<DTex> textures;
+    DevBuf<uint32_t> texels;
+    DevBuf<float> lut;
+    DScene scene;
+    // render state
+    DevBuf<float4> qo[2], qd[2], qthr[2], hit, rad, accum;
+    DevBuf<uint32_t> counters;
+    DevBuf<unsigned long long> stats;
+    DevBuf<int32_t> prim_ids;
+    DevBuf<uint8_t> rgb8;
+    int extend_blocks = 0, shade_blocks = 0;
+    // profiling
+    std::vector<std::pair<cudaEvent_t, int>> marks;  // event recorded AFTER a kernel of that kind
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+
+    cudaEvent_t next_event() {
+        if (events_used == event_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            event_pool.push_back(e);
+        }
+        return event_pool[events_used++];
+    }
+};
+
+}  // namespace
+
+struct rt_gpu_ctx {
+    std::vector<std::unique_ptr<DeviceState>> devs;
+    std::vector<ncclComm_t> comms;
+    bool have_scene = false, have_render = false, profiling = false;
+    rt_render_params last{};
+    rt_stats stats{};
+    uint32_t ray_depth = 0;
+};
+
+namespace {
+
+int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p) {
+    CU_CHECK(cudaSetDevice(d.device));
+    if (int rc = d.nodes.upload(p.scene.nodes, d.stream)) return rc;
+    if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
+    if (int rc = d.lnodes.upload(p.light.nodes, d.stream)) return rc;
+    if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
+    if (int rc = d.attrs.upload(p.attrs, d.stream)) return rc;
+    if (int rc = d.tangents.upload(p.tangents, d.stream)) return rc;
+    if (int rc = d.light_extra.upload(p.light_extra, d.stream)) return rc;
+    if (int rc = d.materials.upload(p.materials, d.stream)) return rc;
+    if (int rc = d.textures.upload(p.textures, d.stream)) return rc;
+    if (int rc = d.texels.upload(p.texels, d.stream)) return rc;
+    std::vector<float> lut(p.gamma_lut, p.gamma_lut + 256);
+    if (int rc = d.lut.upload(lut, d.stream)) return rc;
+    rt::fill_scene_constants(sc, p, d.scene);
+    d.scene.scene.nodes = d.nodes.p;
+    d.scene.scene.tris = d.tris.p;
+    d.scene.light.nodes = d.lnodes.p;
+    d.scene.light.tris = d.ltris.p;
+    d.scene.attrs = d.attrs.p;
+    d.scene.tangents = p.tangents.empty() ? nullptr : d.tangents.p;
+    d.scene.light_extra = d.light_extra.p;
+    d.scene.materials = d.materials.p;
+    d.scene.textures = d.textures.p;
+    d.scene.texels = d.texels.p;
+    CU_CHECK(cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
+rt::Camera make_camera(const DScene &s, uint32_t w, uint32_t h) {
+    rt::Camera c;
+    c.pos = rt::mk3(s.cam_pos[0], s.cam_pos[1], s.cam_pos[2]);
+    c.right = rt::mk3(s.cam_right[0], s.cam_right[1], s.cam_right[2]);
+    c.up = rt::mk3(s.cam_up[0], s.cam_up[1], s.cam_up[2]);
+    c.fwd = rt::mk3(s.cam_fwd[0], s.cam_fwd[1], s.cam_fwd[2]);
+    // tan(fov_x / 2) and Camera::fov_y (scene.h:69-71), evaluated on the host exactly like the reference
+    c.tan_half_x = std::tan(s.fov_x / 2);
+    const float fov_y = std::atan(std::tan(s.fov_x / 2) * static_cast<float>(h) / static_cast<float>(w)) * 2;
+    c.tan_half_y = std::tan(fov_y / 2);
+    c.inv_w2 = 2.0f / static_cast<float>(w);
+    c.inv_h2 = 2.0f / static_cast<float>(h);
+    return c;
+}
+
+void mark(rt_gpu_ctx *ctx, DeviceState &d, int kind) {
+    if (!ctx->profiling) return;
+    cudaEvent_t e = d.next_event();
+    cudaEventRecord(e, d.stream);
+    d.marks.emplace_back(e, kind);
+}
+
+// Enqueue the whole render of samples [s_begin, s_end) on device d (asynchronous).
+int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, uint32_t s_begin, uint32_t s_end,
+                   uint64_t &launches) {
+    CU_CHECK(cudaSetDevice(d.device));
+    const uint32_t W = rp.width, H = rp.height, depth = d.scene.ray_depth;
+    const size_t n_pix = static_cast<size_t>(W) * H;
+    const rt::Camera cam = make_camera(d.scene, W, H);
+    if (int rc = d.accum.alloc(n_pix)) return rc;
+    if (int rc = d.stats.alloc(4)) return rc;
+    CU_CHECK(cudaMemsetAsync(d.stats.p, 0, 4 * sizeof(unsigned long long), d.stream));
+    if (!(rp.flags & RT_FLAG_ACCUMULATE)) CU_CHECK(cudaMemsetAsync(d.accum.p, 0, n_pix * sizeof(float4), d.stream));
+    d.marks.clear();
+    d.events_used = 0;
+    CU_CHECK(cudaEventRecord(d.ev_begin, d.stream));
+    mark(ctx, d, -1);
+
+    if (rp.mode == RT_MODE_PRIMARY_IDS) {
+        if (int rc = d.prim_ids.alloc(n_pix)) return rc;
+        const uint32_t blocks = static_cast<uint32_t>((n_pix + 127) / 128);
+        rt::k_primary_ids<<<blocks, 128, 0, d.stream>>>(cam, d.scene.scene, d.scene.eps, W, H, d.prim_ids.p);
+        ++launches;
+        mark(ctx, d, K_IDS);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
+        return RT_OK;
+    }
+    if (s_end <= s_begin || depth == 0) {  // run_raytracer returns early for ray_depth == 0, raytracer.h:630
+        CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
+        return RT_OK;
+    }
+
+    size_t max_paths = rp.max_paths_in_flight ? rp.max_paths_in_flight : (8u << 20);
+    max_paths = std::max<size_t>(max_paths, 1024);
+    const size_t cap = std::min(max_paths, n_pix * static_cast<size_t>(s_end - s_begin));
+    for (int i = 0; i < 2; ++i) {
+        if (int rc = d.qo[i].alloc(cap)) return rc;
+        if (int rc = d.qd[i].alloc(cap)) return rc;
+        if (int rc = d.qthr[i].alloc(cap)) return rc;
+    }
+    if (int rc = d.hit.alloc(cap)) return rc;
+    if (int rc = d.rad.alloc(cap)) return rc;
+    const size_t n_counters = 3 * static_cast<size_t>(depth) + 1;
+    if (int rc = d.counters.alloc(n_counters)) return rc;
+
+    rt::Queues q;
+    for (int i = 0; i < 2; ++i) {
+        q.o[i] = d.qo[i].p;
+        q.d[i] = d.qd[i].p;
+        q.thr[i] = d.qthr[i].p;
+    }
+    q.hit = d.hit.p;
+    q.rad = d.rad.p;
+    q.count = d.counters.p;
+    q.fetch_ext = d.counters.p + depth + 1;
+    q.fetch_shade = d.counters.p + 2 * depth + 1;
+    q.stats = d.stats.p;
+
+    rt::BatchParams bp;
+    bp.width = W;
+    bp.height = H;
+    bp.k0 = static_cast<uint32_t>(rp.seed);
+    bp.k1 = static_cast<uint32_t>(rp.seed >> 32);
+
+    // batches: all pixels x k samples when the image fits, else pixel chunks x 1 sample
+    const size_t pix_chunk = std::min(n_pix, cap);
+    for (size_t pix0 = 0; pix0 < n_pix; pix0 += pix_chunk) {
+        const uint32_t npix = static_cast<uint32_t>(std::min(pix_chunk, n_pix - pix0));
+        const uint32_t k_max = static_cast<uint32_t>(std::max<size_t>(1, cap / npix));
+        for (uint32_t s0 = s_begin; s0 < s_end; s0 += k_max) {
+            bp.pix0 = static_cast<uint32_t>(pix0);
+            bp.npix = npix;
+            bp.s0 = s0;
+            bp.k = std::min(k_max, s_end - s0);
+            const uint32_t n = bp.npix * bp.k;
+            CU_CHECK(cudaMemsetAsync(d.counters.p, 0, n_counters * sizeof(uint32_t), d.stream));
+            rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q);
+            mark(ctx, d, K_GENERATE);
+            for (uint32_t b = 0; b < depth; ++b) {
+                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.eps, q, b);
+                mark(ctx, d, K_EXTEND);
+                rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b);
+                mark(ctx, d, K_SHADE);
+            }
+            rt::k_accumulate<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.rad.p, d.accum.p);
+            mark(ctx, d, K_ACCUMULATE);
+            launches += 2 + 2 * static_cast<uint64_t>(depth);
+        }
+    }
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rt_gpu_last_error(void) { return g_last_error.c_str(); }
+int rt_gpu_abi_version(void) { return RT_GPU_ABI_VERSION; }
+
+int rt_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device) {
+    if (!out || n_gpus < 1 || first_device < 0) return fail(RT_ERR_INVALID_ARG, "rt_gpu_create: bad arguments");
+    *out = nullptr;
+    const int have = rt_gpu_device_count();
+    if (have < first_device + n_gpus)
+        return fail(RT_ERR_NO_DEVICE, "rt_gpu_create: " + std::to_string(first_device + n_gpus) +
+                                          " CUDA device(s) required, " + std::to_string(have) +
+                                          " usable (this backend has no CPU path)");
+    std::unique_ptr<rt_gpu_ctx> ctx(new rt_gpu_ctx());
+    for (int i = 0; i < n_gpus; ++i) {
+        std::unique_ptr<DeviceState> d(new DeviceState());
+        d->device = first_device + i;
+        CU_CHECK(cudaSetDevice(d->device));
+        cudaDeviceProp prop;
+        CU_CHECK(cudaGetDeviceProperties(&prop, d->device));
+        if (prop.major < 10)
+            return fail(RT_ERR_NO_DEVICE, std::string("rt_gpu_create: device '") + prop.name +
+                                              "' is not sm_100+ (kernels are built for sm_100a only)");
+        d->sm_count = prop.multiProcessorCount;
+        CU_CHECK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaEventCreate(&d->ev_begin));
+        CU_CHECK(cudaEventCreate(&d->ev_end));
+        CU_CHECK(cudaEventCreate(&d->ev_red0));
+        CU_CHECK(cudaEventCreate(&d->ev_red1));
+        int occ_e = 0, occ_s = 0;
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, rt::k_extend, rt::kExtendThreads, 0));
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, rt::k_shade, rt::kShadeThreads, 0));
+        d->extend_blocks = d->sm_count * std::max(occ_e, 1);
+        d->shade_blocks = d->sm_count * std::max(occ_s, 1);
+        ctx->devs.push_back(std::move(d));
+    }
+    if (n_gpus > 1) {
+        if (!g_nccl.load()) return fail(RT_ERR_NCCL, "rt_gpu_create: libnccl.so.2 could not be loaded for a multi-device handle");
+        std::vector<int> ids;
+        for (auto &d : ctx->devs) ids.push_back(d->device);
+        ctx->comms.resize(n_gpus);
+        const int rc = g_nccl.CommInitAll(ctx->comms.data(), n_gpus, ids.data());
+        if (rc != 0) {
+            ctx->comms.clear();
+            return fail(RT_ERR_NCCL, std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        }
+    }
+    *out = ctx.release();
+    return RT_OK;
+}
+
+void rt_gpu_destroy(rt_gpu_ctx *ctx) {
+    if (!ctx) return;
+    for (ncclComm_t c : ctx->comms) g_nccl.CommDestroy(c);
+    for (auto &dp : ctx->devs) {
+        DeviceState &d = *dp;
+        cudaSetDevice(d.device);
+        cudaStreamSynchronize(d.stream);
+        d.nodes.release(); d.lnodes.release(); d.tris.release(); d.ltris.release(); d.attrs.release();
+        d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
+        d.texels.release(); d.lut.release();
+        for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }
+        d.hit.release(); d.rad.release(); d.accum.release(); d.counters.release(); d.stats.release();
+        d.prim_ids.release(); d.rgb8.release();
+        for (cudaEvent_t e : d.event_pool) cudaEventDestroy(e);
+        cudaEventDestroy(d.ev_begin); cudaEventDestroy(d.ev_end);
+        cudaEventDestroy(d.ev_red0); cudaEventDestroy(d.ev_red1);
+        cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
+    if (!ctx || !scene) return fail(RT_ERR_INVALID_ARG, "rt_gpu_upload_scene: null argument");
+    if (scene->abi_version != RT_GPU_ABI_VERSION) return fail(RT_ERR_INVALID_ARG, "rt_gpu_upload_scene: ABI version mismatch");
+    // structural validation (ids in range) before anything is dereferenced on the device
+    for (uint32_t i = 0; i < scene->n_tris; ++i)
+        if (scene->tri_material[i] >= scene->n_materials) return fail(RT_ERR_BAD_SCENE, "material id out of range");
+    for (const rt_bvh_desc *b : {&scene->scene_bvh, &scene->light_bvh}) {
+        if (b->root != RT_NO_CHILD && b->root >= b->n_nodes) return fail(RT_ERR_BAD_SCENE, "BVH root out of range");
+        for (uint32_t i = 0; i < b->n_objects; ++i)
+            if (b->objects[i] >= scene->n_tris) return fail(RT_ERR_BAD_SCENE, "BVH object id out of range");
+        for (uint32_t i = 0; i < b->n_nodes; ++i) {
+            const rt_bvh_node &nd = b->nodes[i];
+            if ((nd.left_child != RT_NO_CHILD && nd.left_child >= b->n_nodes) ||
+                (nd.right_child != RT_NO_CHILD && nd.right_child >= b->n_nodes) || nd.obj_begin > nd.obj_end ||
+                nd.obj_end > b->n_objects)
+                return fail(RT_ERR_BAD_SCENE, "BVH node links out of range");
+        }
+    }
+    for (uint32_t i = 0; i < scene->n_materials; ++i) {
+        const rt_material &m = scene->materials[i];
+        for (int32_t t : {m.color_tex, m.emissive_tex, m.metallic_roughness_tex, m.normal_tex})
+            if (t < -1 || t >= static_cast<int32_t>(scene->n_textures)) return fail(RT_ERR_BAD_SCENE, "texture id out of range");
+    }
+    for (uint32_t i = 0; i < scene->n_textures; ++i) {
+        const rt_texture &t = scene->textures[i];
+        if (!t.width || !t.height || t.offset + static_cast<uint64_t>(t.width) * t.height * 4 > scene->texel_bytes)
+            return fail(RT_ERR_BAD_SCENE, "texture extent out of range");
+    }
+    rt::PackedScene packed;
+    if (int rc = rt::pack_scene(*scene, packed)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    for (auto &d : ctx->devs)
+        if (int rc = upload_to_device(*d, *scene, packed)) return rc;
+    ctx->ray_depth = scene->ray_depth;
+    ctx->have_scene = true;
+    ctx->have_render = false;
+    return RT_OK;
+}
+
+int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params) {
+    if (!ctx || !params) return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: null argument");
+    if (!ctx->have_scene) return fail(RT_ERR_NO_SCENE, "rt_gpu_render: no scene uploaded");
+    rt_render_params rp = *params;
+    if (rp.width == 0 || rp.height == 0 || static_cast<uint64_t>(rp.width) * rp.height > 0x7FFFFFFFull)
+        return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: illegal image size");
+    if (rp.mode == RT_MODE_BEAUTY && rp.samples == 0) return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: samples == 0");
+    if (rp.sample_end == 0) rp.sample_end = rp.samples;
+    if (rp.sample_begin > rp.sample_end) return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: sample_begin > sample_end");
+    const int n = static_cast<int>(ctx->devs.size());
+    const uint32_t total = rp.sample_end - rp.sample_begin;
+    uint64_t launches = 0;
+    // sample-split: device g renders [begin + g*total/n, begin + (g+1)*total/n) of every pixel
+    for (int g = 0; g < n; ++g) {
+        const uint32_t sb = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * g / n);
+        const uint32_t se = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * (g + 1) / n);
+        rt_render_params local = rp;
+        if (rp.mode == RT_MODE_PRIMARY_IDS && g > 0) continue;  // ids: device 0 only
+        if (int rc = enqueue_render(ctx, *ctx->devs[g], local, sb, se, launches)) return rc;
+    }
+    const size_t n_floats = static_cast<size_t>(rp.width) * rp.height * 4;
+    if (n > 1 && rp.mode == RT_MODE_BEAUTY) {
+        for (auto &d : ctx->devs) {
+            CU_CHECK(cudaSetDevice(d->device));
+            CU_CHECK(cudaEventRecord(d->ev_red0, d->stream));
+        }
+        g_nccl.GroupStart();
+        for (int g = 0; g < n; ++g) {
+            DeviceState &d = *ctx->devs[g];
+            const int rc = g_nccl.Reduce(d.accum.p, d.accum.p, n_floats, kNcclFloat32, kNcclSum, 0, ctx->comms[g], d.stream);
+            if (rc != 0) {
+                g_nccl.GroupEnd();
+                return fail(RT_ERR_NCCL, std::string("ncclReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+            }
+        }
+        if (int rc = g_nccl.GroupEnd()) return fail(RT_ERR_NCCL, std::string("ncclGroupEnd: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        for (auto &d : ctx->devs) {
+            CU_CHECK(cudaSetDevice(d->device));
+            CU_CHECK(cudaEventRecord(d->ev_red1, d->stream));
+        }
+    }
+    rt_stats st;
+    std::memset(&st, 0, sizeof st);
+    for (int g = 0; g < n; ++g) {
+        DeviceState &d = *ctx->devs[g];
+        if (rp.mode == RT_MODE_PRIMARY_IDS && g > 0) continue;
+        CU_CHECK(cudaSetDevice(d.device));
+        CU_CHECK(cudaStreamSynchronize(d.stream));
+        float ms = 0.0f;
+        CU_CHECK(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
+        st.render_ms = std::max(st.render_ms, static_cast<double>(ms));
+        if (n > 1 && rp.mode == RT_MODE_BEAUTY) {
+            CU_CHECK(cudaEventElapsedTime(&ms, d.ev_red0, d.ev_red1));
+            st.reduce_ms = std::max(st.reduce_ms, static_cast<double>(ms));
+        }
+        unsigned long long hs[4] = {0, 0, 0, 0};
+        if (d.stats.p) CU_CHECK(cudaMemcpy(hs, d.stats.p, sizeof hs, cudaMemcpyDeviceToHost));
+        st.extension_rays += hs[0];
+        st.light_pdf_rays += hs[1];
+        st.shades += hs[2];
+        st.samples += hs[3];
+        if (ctx->profiling) {
+            double per_kind[K_COUNT] = {0};
+            for (size_t i = 1; i < d.marks.size(); ++i) {
+                float dt = 0.0f;
+                cudaEventElapsedTime(&dt, d.marks[i - 1].first, d.marks[i].first);
+                if (d.marks[i].second >= 0) per_kind[d.marks[i].second] += dt;
+            }
+            for (int k = 0; k < K_COUNT; ++k) st.kernel_ms[k] = std::max(st.kernel_ms[k], per_kind[k]);
+        }
+    }
+    st.kernel_launches = launches;
+    ctx->stats = st;
+    ctx->last = rp;
+    ctx->have_render = true;
+    return RT_OK;
+}
+
+int rt_gpu_readback(rt_gpu_ctx *ctx, float *rgb_mean, int32_t *prim_ids, rt_stats *stats) {
+    if (!ctx) return fail(RT_ERR_INVALID_ARG, "rt_gpu_readback: null handle");
+    if (!ctx->have_render) return fail(RT_ERR_NO_RENDER, "rt_gpu_readback: nothing rendered");
+    DeviceState &d = *ctx->devs[0];
+    CU_CHECK(cudaSetDevice(d.device));
+    const size_t n_pix = static_cast<size_t>(ctx->last.width) * ctx->last.height;
+    if (rgb_mean) {
+        if (ctx->last.mode != RT_MODE_BEAUTY) return fail(RT_ERR_NO_RENDER, "rt_gpu_readback: last render was not a beauty render");
+        std::vector<float4> host(n_pix);
+        CU_CHECK(cudaMemcpy(host.data(), d.accum.p, n_pix * sizeof(float4), cudaMemcpyDeviceToHost));
+        const float samples = static_cast<float>(ctx->last.samples);
+        for (size_t i = 0; i < n_pix; ++i) {  // `res / samples`, raytracer.h:626
+            rgb_mean[i * 3 + 0] = host[i].x / samples;
+            rgb_mean[i * 3 + 1] = host[i].y / samples;
+            rgb_mean[i * 3 + 2] = host[i].z / samples;
+        }
+    }
+    if (prim_ids) {
+        if (ctx->last.mode != RT_MODE_PRIMARY_IDS) return fail(RT_ERR_NO_RENDER, "rt_gpu_readback: last render was not a primary-id render");
+        CU_CHECK(cudaMemcpy(prim_ids, d.prim_ids.p, n_pix * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    if (stats) *stats = ctx->stats;
+    return RT_OK;
+}
+
+int rt_gpu_accum_device_ptr(rt_gpu_ctx *ctx, void **dptr, size_t *n_floats) {
+    if (!ctx || !dptr) return fail(RT_ERR_INVALID_ARG, "rt_gpu_accum_device_ptr: null argument");
+    if (!ctx->have_render || ctx->last.mode != RT_MODE_BEAUTY) return fail(RT_ERR_NO_RENDER, "rt_gpu_accum_device_ptr: no beauty render");
+    *dptr = ctx->devs[0]->accum.p;
+    if (n_floats) *n_floats = static_cast<size_t>(ctx->last.width) * ctx->last.height * 4;
+    return RT_OK;
+}
+
+int rt_gpu_readback_rgb8(rt_gpu_ctx *ctx, uint8_t *rgb8) {
+    if (!ctx || !rgb8) return fail(RT_ERR_INVALID_ARG, "rt_gpu_readback_rgb8: null argument");
+    if (!ctx->have_render || ctx->last.mode != RT_MODE_BEAUTY) return fail(RT_ERR_NO_RENDER, "rt_gpu_readback_rgb8: no beauty render");
+    DeviceState &d = *ctx->devs[0];
+    CU_CHECK(cudaSetDevice(d.device));
+    const uint32_t n_pix = ctx->last.width * ctx->last.height;
+    if (int rc = d.rgb8.alloc(static_cast<size_t>(n_pix) * 3)) return rc;
+    rt::k_tonemap<<<(n_pix + 255) / 256, 256, 0, d.stream>>>(d.accum.p, static_cast<float>(ctx->last.samples), n_pix, d.rgb8.p);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(rgb8, d.rgb8.p, static_cast<size_t>(n_pix) * 3, cudaMemcpyDeviceToHost, d.stream));
+    CU_CHECK(cudaStreamSynchronize(d.stream));
+    return RT_OK;
+}
+
+int rt_gpu_fp32_peak(rt_gpu_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return fail(RT_ERR_INVALID_ARG, "rt_gpu_fp32_peak: null argument");
+    DeviceState &d = *ctx->devs[0];
+    CU_CHECK(cudaSetDevice(d.device));
+    if (int rc = d.lut.alloc(256)) return rc;
+    const int iters = 1 << 14, threads = 256, blocks = d.sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_CHECK(cudaEventRecord(d.ev_red0, d.stream));
+        rt::k_fma_peak<<<blocks, threads, 0, d.stream>>>(d.lut.p, 0.999f, 1e-4f, iters);
+        CU_CHECK(cudaEventRecord(d.ev_red1, d.stream));
+        CU_CHECK(cudaStreamSynchronize(d.stream));
+        float ms = 0.0f;
+        CU_CHECK(cudaEventElapsedTime(&ms, d.ev_red0, d.ev_red1));
+        const double flops = 2.0 * 16.0 * iters * static_cast<double>(threads) * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    *tflops = best;
+    return RT_OK;
+}
+
+int rt_gpu_set_profiling(rt_gpu_ctx *ctx, int enable) {
+    if (!ctx) return fail(RT_ERR_INVALID_ARG, "rt_gpu_set_profiling: null handle");
+    ctx->profiling = enable != 0;
+    return RT_OK;
+}
+
+}  // extern "C"

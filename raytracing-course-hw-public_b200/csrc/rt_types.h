@@ -1,0 +1,100 @@
+// rt_types.h — device-side scene layout (what rt_gpu_upload_scene builds from an rt_scene_desc).
+//
+// The reference keeps a pointer-linked AoS (Object* -> material -> Texture*, 208 B per triangle,
+// 40 B nodes that hold their own box; src/bvh.h:157-168, src/geometry.h:604-659).  For the GPU
+// everything is re-packed into 16-byte-aligned records fetched with 128-bit loads:
+//
+//   DNode  64 B  one per INNER node of the reference tree: both children's boxes + child links.
+//                The reference tests both child boxes at the parent (bvh.h:205-212), so one
+//                64 B fetch replaces two 40 B node fetches.
+//   DTri   48 B  triangle in BVH order: a, (b-a), (c-a) + scene.objects id + end-of-leaf flag.
+//   DAttr  64 B  per-vertex normals + uv + material id, BVH order (read once per shade).
+//   DMat   64 B  deduplicated material.
+//
+// A child link >= 0 is an inner-node index; < 0 is a leaf: ~link = index of its first DTri, the
+// leaf ends at the first DTri whose `id_last` has bit 31 set.
+#ifndef RT_TYPES_H
+#define RT_TYPES_H
+
+#include <stdint.h>
+
+#define RT_STACK_SIZE 64        /* BVH::build max_depth = 64, bvh.h:371 */
+#define RT_LINK_NONE 0x7FFFFFFF /* empty BVH */
+#define RT_LAST_BIT 0x80000000u
+
+struct alignas(16) DNode {
+    // lo/hi of the left (l) and right (r) child boxes
+    float lminx, lminy, lminz, lmaxx;
+    float lmaxy, lmaxz, rminx, rminy;
+    float rminz, rmaxx, rmaxy, rmaxz;
+    int32_t left, right;  // links
+    int32_t pad0, pad1;
+};
+
+struct alignas(16) DTri {
+    float ax, ay, az;
+    uint32_t id_last;  // scene.objects index | RT_LAST_BIT on the last triangle of a leaf
+    float e1x, e1y, e1z, pad0;  // b - a  (triangle::v, geometry.h:473)
+    float e2x, e2y, e2z, pad1;  // c - a  (triangle::u, geometry.h:475)
+};
+
+struct alignas(16) DAttr {
+    float n0x, n0y, n0z, uv0x;
+    float n1x, n1y, n1z, uv0y;
+    float n2x, n2y, n2z, uv1x;
+    float uv1y, uv2x, uv2y;
+    uint32_t material;
+};
+
+struct alignas(16) DTangent {  // only when some tangent differs from (1,0,0)
+    float t0x, t0y, t0z, t1x;
+    float t1y, t1z, t2x, t2y;
+    float t2z, pad0, pad1, pad2;
+};
+
+struct alignas(16) DMat {
+    float color[4];
+    float emission[3];
+    float roughness;
+    float metallic, ior;
+    int32_t color_tex, emissive_tex;
+    int32_t mr_tex, normal_tex;
+    int32_t pad0, pad1;
+};
+
+struct alignas(16) DTex {
+    uint32_t offset;  // in texels (uint32 RGBA8) from the texel pool
+    uint32_t width, height;
+    uint32_t pad;
+};
+
+struct alignas(16) DLight {  // light triangle extras, light-BVH order
+    float nx, ny, nz;  // triangle::normal (geometry.h:477)
+    float area;        // triangle::square (geometry.h:481)
+};
+
+struct DBvh {
+    const DNode *nodes;
+    const DTri *tris;
+    int32_t root;  // link; RT_LINK_NONE when empty
+    uint32_t n_tris;
+};
+
+struct DScene {
+    DBvh scene;
+    DBvh light;
+    const DAttr *attrs;         // scene-BVH order
+    const DTangent *tangents;   // scene-BVH order or nullptr
+    const DLight *light_extra;  // light-BVH order
+    const DMat *materials;
+    const DTex *textures;
+    const uint32_t *texels;
+    uint32_t n_lights;
+    uint32_t ray_depth;
+    float eps, min_roughness, vndf_factor;
+    float bg[3];
+    float cam_pos[3], cam_right[3], cam_up[3], cam_fwd[3];
+    float fov_x;
+};
+
+#endif  // RT_TYPES_H

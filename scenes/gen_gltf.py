@@ -195,7 +195,7 @@ def corridor(name, scale, lights):
     W, L, H = 16.0, 60.0, 12.0
     s = lambda n: max(2, int(round(n * scale)))
 
-    tex = g.texture(name + "_base.ppm", ppm_bytes(checker_texture(rng)))
+    tex = g.texture(name + "_base.ppm", ppm_bytes(checker_texture(rng, 512 if scale >= 1.0 else 128)))
     m_floor = g.material(pbrMetallicRoughness={"baseColorTexture": {"index": tex}, "metallicFactor": 0.0,
                                                "roughnessFactor": 0.9})
     m_wall = g.material(pbrMetallicRoughness={"baseColorFactor": [0.9, 0.8, 0.7, 1.0],

@@ -1,0 +1,133 @@
+// hostcheck.cpp — TEST-ONLY host compilation of the device math header (csrc/pt_core.cuh) and of the
+// scene re-packing (csrc/repack.h).  It lets the CPU test-suite (`-m "not gpu"`) compare the exact
+// functions the CUDA kernels call (traversal, hit shading data, samplers, pdfs, BRDF, Philox lanes)
+// with the oracle without a GPU.  It is NOT a render path of the product: librt_gpu.so does not
+// contain or call any of this, and nothing outside tests/ builds or loads it.
+#include <cstring>
+#include <vector>
+
+#include "pt_core.cuh"
+#include "repack.h"
+#include "rt_gpu.h"
+
+using namespace rt;
+
+namespace {
+struct HostScene {
+    PackedScene p;
+    DScene d;
+};
+
+int build(const rt_scene_desc *sc, HostScene &hs) {
+    if (int rc = pack_scene(*sc, hs.p)) return rc;
+    fill_scene_constants(*sc, hs.p, hs.d);
+    hs.d.scene.nodes = hs.p.scene.nodes.data();
+    hs.d.scene.tris = hs.p.scene.tris.data();
+    hs.d.light.nodes = hs.p.light.nodes.data();
+    hs.d.light.tris = hs.p.light.tris.data();
+    hs.d.attrs = hs.p.attrs.data();
+    hs.d.tangents = hs.p.tangents.empty() ? nullptr : hs.p.tangents.data();
+    hs.d.light_extra = hs.p.light_extra.data();
+    hs.d.materials = hs.p.materials.data();
+    hs.d.textures = hs.p.textures.data();
+    hs.d.texels = hs.p.texels.data();
+    return 0;
+}
+
+Camera make_camera(const DScene &d, uint32_t w, uint32_t h) {
+    Camera c;
+    c.pos = mk3(d.cam_pos[0], d.cam_pos[1], d.cam_pos[2]);
+    c.right = mk3(d.cam_right[0], d.cam_right[1], d.cam_right[2]);
+    c.up = mk3(d.cam_up[0], d.cam_up[1], d.cam_up[2]);
+    c.fwd = mk3(d.cam_fwd[0], d.cam_fwd[1], d.cam_fwd[2]);
+    c.tan_half_x = tanf(d.fov_x / 2);
+    const float fov_y = atanf(tanf(d.fov_x / 2) * (float)h / (float)w) * 2;
+    c.tan_half_y = tanf(fov_y / 2);
+    c.inv_w2 = 2.0f / (float)w;
+    c.inv_h2 = 2.0f / (float)h;
+    return c;
+}
+}  // namespace
+
+extern "C" {
+
+int hc_primary_ids(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    const Camera cam = make_camera(hs.d, w, h);
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
+            const Hit hit = closest_hit(hs.d.scene, cam.pos, dir, hs.d.eps);
+            ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
+        }
+    return 0;
+}
+
+// Surface of the primary hit per pixel, 18 floats in the layout of `ref_tool hitinfo`.
+int hc_hitinfo(const rt_scene_desc *sc, uint32_t w, uint32_t h, float *out) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    const Camera cam = make_camera(hs.d, w, h);
+    std::memset(out, 0, (size_t)w * h * 18 * sizeof(float));
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
+            const Hit hit = closest_hit(hs.d.scene, cam.pos, dir, hs.d.eps);
+            if (hit.tri < 0) continue;
+            const Surface sf = make_surface(hs.d, hs.p.gamma_lut, hit, dir);
+            float *o = out + ((size_t)y * w + x) * 18;
+            o[0] = hit.t;
+            o[1] = sf.ng.x; o[2] = sf.ng.y; o[3] = sf.ng.z;
+            o[4] = sf.ns.x; o[5] = sf.ns.y; o[6] = sf.ns.z;
+            o[7] = sf.color.x; o[8] = sf.color.y; o[9] = sf.color.z; o[10] = sf.alpha;
+            o[11] = sf.emission.x; o[12] = sf.emission.y; o[13] = sf.emission.z;
+            o[14] = sf.metallic; o[15] = sf.roughness;
+            o[16] = 0.0f;  // is_inside is folded into the normals
+            o[17] = sf.ior;
+        }
+    return 0;
+}
+
+// Sequential per-sample loop over the same state transition the wavefront kernels apply.
+int hc_render(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint32_t samples, uint32_t s_begin, uint32_t s_end,
+              uint64_t seed, float *rgb_mean, uint64_t *counters /* ext rays, light rays */) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    const Camera cam = make_camera(hs.d, w, h);
+    uint64_t ext = 0, lrays = 0;
+    for (uint32_t pix = 0; pix < w * h; ++pix) {
+        f3 sum = mk3(0, 0, 0);
+        for (uint32_t s = s_begin; s < s_end; ++s) {
+            const RngKey key{pix, s, (uint32_t)seed, (uint32_t)(seed >> 32)};
+            const u4 j = rng_jitter(key);
+            f3 o = cam.pos;
+            f3 d = camera_dir(cam, (float)(pix % w) + u01(j.x), (float)(pix / w) + u01(j.y));
+            f3 thr = mk3(1, 1, 1), rad = mk3(0, 0, 0);
+            for (uint32_t b = 0; b < hs.d.ray_depth; ++b) {
+                const Hit hit = closest_hit(hs.d.scene, o, d, hs.d.eps);
+                ++ext;
+                uint32_t lr = 0;
+                const bool alive = shade_bounce(hs.d, hs.p.gamma_lut, key, b, b + 1 == hs.d.ray_depth, hit, o, d, thr, rad, lr);
+                lrays += lr;
+                if (!alive) break;
+            }
+            sum = sum + sanitize(rad);
+        }
+        rgb_mean[(size_t)pix * 3 + 0] = sum.x / (float)samples;
+        rgb_mean[(size_t)pix * 3 + 1] = sum.y / (float)samples;
+        rgb_mean[(size_t)pix * 3 + 2] = sum.z / (float)samples;
+    }
+    if (counters) {
+        counters[0] = ext;
+        counters[1] = lrays;
+    }
+    return 0;
+}
+
+void hc_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+    const u4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+}  // extern "C"
