@@ -32,6 +32,7 @@ struct BatchParams {
     uint32_t k;         // samples per pixel in this batch
     uint32_t width, height;
     uint32_t k0, k1;    // Philox key
+    uint32_t centre;    // 1: pixel-centre rays without jitter (gen_ray(camera, x, y), raytracer.h:516-525)
 };
 
 struct Queues {
@@ -79,25 +80,169 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
     const uint32_t sample = bp.s0 + j;
     const uint32_t py = pixel / bp.width, px = pixel - py * bp.width;
     const RngKey key{pixel, sample, bp.k0, bp.k1};
-    const u4 r = rng_jitter(key);
-    const f3 dir = camera_dir(cam, static_cast<float>(px) + u01(r.x), static_cast<float>(py) + u01(r.y));
+    float jx = 0.5f, jy = 0.5f;
+    if (!bp.centre) {
+        const u4 r = rng_jitter(key);
+        jx = u01(r.x);
+        jy = u01(r.y);
+    }
+    const f3 dir = camera_dir(cam, static_cast<float>(px) + jx, static_cast<float>(py) + jy);
     q.o[0][slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel));
     q.d[0][slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample));
     q.thr[0][slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
+// ---- k_extend -----------------------------------------------------------------------------------------
+// Closest-hit traversal, warp-synchronous "while-while" with one postponed leaf per lane (Aila & Laine
+// 2009 style speculative traversal) and per-lane ray refill:
+//   * every loop condition is a warp vote (__any_sync / __ballot_sync), so the 32 lanes re-converge at
+//     each phase boundary instead of drifting apart (the naive per-thread loop ran its triangle tests
+//     with 2 of 32 lanes active);
+//   * inner phase: lanes descend inner nodes; the first leaf a lane meets is postponed and the lane keeps
+//     descending speculatively; a lane that meets a second leaf waits.  The phase ends when no lane is
+//     still looking for its first leaf;
+//   * leaf phase: all postponed leaves are intersected together, triangle by triangle;
+//   * a lane whose ray is finished stores its hit and takes the next ray from a warp-local block of
+//     kRayBlock queue entries (one atomicAdd per block), ranks handed out with __ballot_sync/__popc.
+// Visiting order (near child first, ties left first, bvh.h:216) and strictly-closer-wins (bvh.h:132)
+// are those of closest_hit() in pt_core.cuh, so both give the same hit.
+constexpr int32_t kLinkDone = static_cast<int32_t>(0x80000000u);
+constexpr uint32_t kRayBlock = 128;
+constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+
 __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, Queues q, uint32_t bounce) {
+    const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
     const float4 *__restrict__ qo = q.o[bounce & 1];
     const float4 *__restrict__ qd = q.d[bounce & 1];
+    uint32_t *cursor = q.fetch_ext + bounce;
+    const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    int32_t stack_link[RT_STACK_SIZE];
+    float stack_t[RT_STACK_SIZE];
+    int sp = 0;
+    int32_t link = kLinkDone;  // >= 0 inner node, < 0 leaf (~first triangle), kLinkDone = nothing left
+    int32_t leaf = 0;          // postponed leaf link (always < 0) or 0 = none
+    uint32_t ray = kNoRay;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1);
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0.0f;
+    best.tri = -1;
+    uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
+    bool exhausted = false;                 // warp-uniform
+
+    auto pop = [&]() {
+        link = kLinkDone;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] < best.t) {  // bvh.h:221: the far child is visited only while best is farther
+                link = stack_link[sp];
+                break;
+            }
+        }
+    };
+
     for (;;) {
-        const uint32_t i = warp_fetch(q.fetch_ext + bounce);
-        if (i - lane_id() >= count) break;
-        if (i < count) {
-            const float4 o = qo[i], d = qd[i];
-            const Hit h = closest_hit(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), eps);
-            q.hit[i] = make_float4(h.t, h.b, h.c, __int_as_float(h.tri));
+        // ---- retire finished rays, refill idle lanes ---------------------------------------------------
+        const bool idle = link == kLinkDone && leaf == 0;
+        if (idle && ray != kNoRay) {
+            q.hit[ray] = make_float4(best.t, best.b, best.c, __int_as_float(best.tri));
+            ray = kNoRay;
+        }
+        const uint32_t m_idle = __ballot_sync(FULL, idle);
+        if (m_idle) {
+            if (pool_next == pool_end && !exhausted) {  // one atomicAdd per kRayBlock rays
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, kRayBlock);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= count) {
+                    exhausted = true;
+                } else {
+                    pool_next = base;
+                    pool_end = base + kRayBlock < count ? base + kRayBlock : count;
+                }
+            }
+            const uint32_t avail = pool_end - pool_next;
+            const uint32_t n_idle = static_cast<uint32_t>(__popc(m_idle));
+            const uint32_t take = n_idle < avail ? n_idle : avail;
+            const uint32_t rank = static_cast<uint32_t>(__popc(m_idle & lt_mask));
+            if (idle && rank < take) {
+                ray = pool_next + rank;
+                const float4 o4 = qo[ray], d4 = qd[ray];
+                o = mk3(o4.x, o4.y, o4.z);
+                d = mk3(d4.x, d4.y, d4.z);
+                idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                best.t = INFINITY;
+                best.b = best.c = 0.0f;
+                best.tri = -1;
+                sp = 0;
+                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
+                if (link < 0 && link != kLinkDone) {  // the root itself is a leaf
+                    leaf = link;
+                    link = kLinkDone;
+                }
+            }
+            pool_next += take;
+            if (avail == 0 && m_idle == FULL) break;  // queue drained and nothing in flight
+        }
+
+        // ---- inner phase -------------------------------------------------------------------------------
+        for (;;) {
+            const bool searching = link >= 0 && leaf == 0;
+            if (!__any_sync(FULL, searching)) break;
+            if (link >= 0) {
+                const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
+                const f4 n0 = ld4(p), n1 = ld4(p + 16), n2 = ld4(p + 32), n3 = ld4(p + 48);
+                const float dl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, idir, eps);
+                const float dr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, idir, eps);
+                const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
+                const bool hl = dl >= 0.0f && dl < best.t, hr = dr >= 0.0f && dr < best.t;
+                if (hl && hr) {
+                    const bool swap = dl > dr;
+                    stack_link[sp] = swap ? ll : lr;
+                    stack_t[sp] = swap ? dl : dr;
+                    ++sp;
+                    link = swap ? lr : ll;
+                } else if (hl || hr) {
+                    link = hl ? ll : lr;
+                } else {
+                    pop();
+                }
+                if (link < 0 && link != kLinkDone && leaf == 0) {  // postpone the first leaf, keep descending
+                    leaf = link;
+                    pop();
+                }
+            }
+        }
+
+        // ---- leaf phase: all postponed leaves, triangle by triangle ------------------------------------
+        {
+            uint32_t k = static_cast<uint32_t>(~leaf);
+            bool more = leaf != 0;
+            while (__any_sync(FULL, more)) {
+                if (more) {
+                    const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+                    const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+                    float t, b, c;
+                    if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, eps, t, b, c) &&
+                        t < best.t) {
+                        best.t = t;
+                        best.b = b;
+                        best.c = c;
+                        best.tri = static_cast<int32_t>(k);
+                    }
+                    more = !(f2u(t0.w) & RT_LAST_BIT);
+                    ++k;
+                }
+            }
+            leaf = 0;
+            if (link < 0 && link != kLinkDone) {  // a lane that was waiting with a second leaf
+                leaf = link;
+                pop();
+            }
         }
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(q.stats + 0, static_cast<unsigned long long>(count));
@@ -185,15 +330,13 @@ __global__ void __launch_bounds__(256) k_accumulate(BatchParams bp, const float4
     accum[bp.pix0 + p] = a;
 }
 
-// RT_MODE_PRIMARY_IDS: pixel-centre rays (gen_ray(camera, x, y), raytracer.h:516-525) -> scene.objects id
-__global__ void __launch_bounds__(128) k_primary_ids(Camera cam, DBvh bvh, float eps, uint32_t width, uint32_t height,
-                                                     int32_t *__restrict__ ids) {
+// RT_MODE_PRIMARY_IDS: hits of the pixel-centre rays (traced by k_extend like any other ray) -> scene.objects id
+__global__ void __launch_bounds__(256) k_ids_from_hits(BatchParams bp, const float4 *__restrict__ hit, const DTri *__restrict__ tris,
+                                                       int32_t *__restrict__ ids) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= width * height) return;
-    const uint32_t y = p / width, x = p - y * width;
-    const f3 dir = camera_dir(cam, static_cast<float>(x) + 0.5f, static_cast<float>(y) + 0.5f);
-    const Hit h = closest_hit(bvh, cam.pos, dir, eps);
-    ids[p] = h.tri < 0 ? -1 : static_cast<int32_t>(bvh.tris[h.tri].id_last & ~RT_LAST_BIT);
+    if (p >= bp.npix) return;
+    const int32_t tri = __float_as_int(hit[p].w);
+    ids[bp.pix0 + p] = tri < 0 ? -1 : static_cast<int32_t>(tris[tri].id_last & ~RT_LAST_BIT);
 }
 
 // Device-side Image::set_pixel (image.h:40-82): mean -> ACES -> gamma 1/2.2 -> x255 -> clamp -> round

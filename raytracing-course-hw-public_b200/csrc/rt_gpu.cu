@@ -208,27 +208,24 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     if (int rc = d.accum.alloc(n_pix)) return rc;
     if (int rc = d.stats.alloc(4)) return rc;
     CU_CHECK(cudaMemsetAsync(d.stats.p, 0, 4 * sizeof(unsigned long long), d.stream));
-    if (!(rp.flags & RT_FLAG_ACCUMULATE)) CU_CHECK(cudaMemsetAsync(d.accum.p, 0, n_pix * sizeof(float4), d.stream));
+    const bool ids_mode = rp.mode == RT_MODE_PRIMARY_IDS;
+    if (!ids_mode && !(rp.flags & RT_FLAG_ACCUMULATE))
+        CU_CHECK(cudaMemsetAsync(d.accum.p, 0, n_pix * sizeof(float4), d.stream));
     d.marks.clear();
     d.events_used = 0;
     CU_CHECK(cudaEventRecord(d.ev_begin, d.stream));
     mark(ctx, d, -1);
 
-    if (rp.mode == RT_MODE_PRIMARY_IDS) {
-        if (int rc = d.prim_ids.alloc(n_pix)) return rc;
-        const uint32_t blocks = static_cast<uint32_t>((n_pix + 127) / 128);
-        rt::k_primary_ids<<<blocks, 128, 0, d.stream>>>(cam, d.scene.scene, d.scene.eps, W, H, d.prim_ids.p);
-        ++launches;
-        mark(ctx, d, K_IDS);
-        CU_CHECK(cudaGetLastError());
-        CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
-        return RT_OK;
-    }
-    if (s_end <= s_begin || depth == 0) {  // run_raytracer returns early for ray_depth == 0, raytracer.h:630
+    if (!ids_mode && (s_end <= s_begin || depth == 0)) {  // run_raytracer returns early for ray_depth == 0, raytracer.h:630
         CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
         return RT_OK;
     }
 
+    if (ids_mode) {
+        if (int rc = d.prim_ids.alloc(n_pix)) return rc;
+        s_begin = 0;
+        s_end = 1;
+    }
     size_t max_paths = rp.max_paths_in_flight ? rp.max_paths_in_flight : (8u << 20);
     max_paths = std::max<size_t>(max_paths, 1024);
     const size_t cap = std::min(max_paths, n_pix * static_cast<size_t>(s_end - s_begin));
@@ -239,7 +236,8 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     }
     if (int rc = d.hit.alloc(cap)) return rc;
     if (int rc = d.rad.alloc(cap)) return rc;
-    const size_t n_counters = 3 * static_cast<size_t>(depth) + 1;
+    const uint32_t qdepth = std::max(depth, 1u);
+    const size_t n_counters = 3 * static_cast<size_t>(qdepth) + 1;
     if (int rc = d.counters.alloc(n_counters)) return rc;
 
     rt::Queues q;
@@ -251,8 +249,8 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     q.hit = d.hit.p;
     q.rad = d.rad.p;
     q.count = d.counters.p;
-    q.fetch_ext = d.counters.p + depth + 1;
-    q.fetch_shade = d.counters.p + 2 * depth + 1;
+    q.fetch_ext = d.counters.p + qdepth + 1;
+    q.fetch_shade = d.counters.p + 2 * qdepth + 1;
     q.stats = d.stats.p;
 
     rt::BatchParams bp;
@@ -260,6 +258,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     bp.height = H;
     bp.k0 = static_cast<uint32_t>(rp.seed);
     bp.k1 = static_cast<uint32_t>(rp.seed >> 32);
+    bp.centre = ids_mode ? 1u : 0u;
 
     // batches: all pixels x k samples when the image fits, else pixel chunks x 1 sample
     const size_t pix_chunk = std::min(n_pix, cap);
@@ -275,6 +274,14 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
             CU_CHECK(cudaMemsetAsync(d.counters.p, 0, n_counters * sizeof(uint32_t), d.stream));
             rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q);
             mark(ctx, d, K_GENERATE);
+            if (ids_mode) {  // pixel-centre rays through the same traversal kernel, then hit -> scene.objects id
+                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.eps, q, 0);
+                mark(ctx, d, K_EXTEND);
+                rt::k_ids_from_hits<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.hit.p, d.scene.scene.tris, d.prim_ids.p);
+                mark(ctx, d, K_IDS);
+                launches += 3;
+                continue;
+            }
             for (uint32_t b = 0; b < depth; ++b) {
                 rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.eps, q, b);
                 mark(ctx, d, K_EXTEND);
