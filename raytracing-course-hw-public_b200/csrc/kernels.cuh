@@ -111,6 +111,15 @@ constexpr int32_t kLinkDone = static_cast<int32_t>(0x80000000u);
 constexpr uint32_t kRayBlock = 128;
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
+// MUFU.RCP (1 ulp): one instruction instead of the IEEE division's Newton step + slow path
+__device__ __forceinline__ float rcp_rn(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, Queues q, uint32_t bounce) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
@@ -120,17 +129,14 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    int32_t stack_link[RT_STACK_SIZE];
-    float stack_t[RT_STACK_SIZE];
+    float2 stack[RT_STACK_SIZE];  // (link bits, entry distance) of postponed far children
     int sp = 0;
     int32_t link = kLinkDone;  // >= 0 inner node, < 0 leaf (~first triangle), kLinkDone = nothing left
     int32_t leaf = 0;          // postponed leaf link (always < 0) or 0 = none
     uint32_t ray = kNoRay;
-    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1);
-    Hit best;
-    best.t = INFINITY;
-    best.b = best.c = 0.0f;
-    best.tri = -1;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1), ood = mk3(0, 0, 0);
+    float best_t = INFINITY, best_b = 0.0f, best_c = 0.0f;
+    int32_t best_tri = -1;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
 
@@ -138,8 +144,9 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
         link = kLinkDone;
         while (sp > 0) {
             --sp;
-            if (stack_t[sp] < best.t) {  // bvh.h:221: the far child is visited only while best is farther
-                link = stack_link[sp];
+            const float2 e = stack[sp];
+            if (e.y < best_t) {  // bvh.h:221: the far child is visited only while best is farther
+                link = __float_as_int(e.x);
                 break;
             }
         }
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
         // ---- retire finished rays, refill idle lanes ---------------------------------------------------
         const bool idle = link == kLinkDone && leaf == 0;
         if (idle && ray != kNoRay) {
-            q.hit[ray] = make_float4(best.t, best.b, best.c, __int_as_float(best.tri));
+            q.hit[ray] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
             ray = kNoRay;
         }
         const uint32_t m_idle = __ballot_sync(FULL, idle);
@@ -174,10 +181,11 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
                 const float4 o4 = qo[ray], d4 = qd[ray];
                 o = mk3(o4.x, o4.y, o4.z);
                 d = mk3(d4.x, d4.y, d4.z);
-                idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                best.t = INFINITY;
-                best.b = best.c = 0.0f;
-                best.tri = -1;
+                idir = mk3(rcp_rn(d.x), rcp_rn(d.y), rcp_rn(d.z));
+                ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+                best_t = INFINITY;
+                best_b = best_c = 0.0f;
+                best_tri = -1;
                 sp = 0;
                 link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
                 if (link < 0 && link != kLinkDone) {  // the root itself is a leaf
@@ -195,19 +203,33 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
             if (!__any_sync(FULL, searching)) break;
             if (link >= 0) {
                 const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
-                const f4 n0 = ld4(p), n1 = ld4(p + 16), n2 = ld4(p + 32), n3 = ld4(p + 48);
-                const float dl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, idir, eps);
-                const float dr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, idir, eps);
+                const f8 na = ld8(p), nb = ld8(p + 32);  // 64 B node = two 256-bit loads
+                const f4 n0 = f4{na.a, na.b, na.c, na.d}, n1 = f4{na.e, na.f, na.g, na.h};
+                const f4 n2 = f4{nb.a, nb.b, nb.c, nb.d}, n3 = f4{nb.e, nb.f, nb.g, nb.h};
+                // slab test of both children (bvh.h:137-152) in fused form t = plane * (1/d) - o/d; the
+                // interval is clipped to [eps, best_t] inside the min/max chain (hit <=> lo <= hi), which
+                // visits exactly the boxes `t_min <= t_max && t_max >= eps && max(t_min, eps) < best` does,
+                // plus harmless ties with best_t.
+                const float lx0 = fmaf(n0.x, idir.x, -ood.x), lx1 = fmaf(n0.w, idir.x, -ood.x);
+                const float ly0 = fmaf(n0.y, idir.y, -ood.y), ly1 = fmaf(n1.x, idir.y, -ood.y);
+                const float lz0 = fmaf(n0.z, idir.z, -ood.z), lz1 = fmaf(n1.y, idir.z, -ood.z);
+                const float rx0 = fmaf(n1.z, idir.x, -ood.x), rx1 = fmaf(n2.y, idir.x, -ood.x);
+                const float ry0 = fmaf(n1.w, idir.y, -ood.y), ry1 = fmaf(n2.z, idir.y, -ood.y);
+                const float rz0 = fmaf(n2.x, idir.z, -ood.z), rz1 = fmaf(n2.w, idir.z, -ood.z);
+                const float dl = fmaxf(fmax3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), eps);
+                const float el = fminf(fmin3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1)), best_t);
+                const float dr = fmaxf(fmax3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), eps);
+                const float er = fminf(fmin3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1)), best_t);
+                const bool hl = dl <= el, hr = dr <= er;
                 const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
-                const bool hl = dl >= 0.0f && dl < best.t, hr = dr >= 0.0f && dr < best.t;
-                if (hl && hr) {
-                    const bool swap = dl > dr;
-                    stack_link[sp] = swap ? ll : lr;
-                    stack_t[sp] = swap ? dl : dr;
-                    ++sp;
-                    link = swap ? lr : ll;
-                } else if (hl || hr) {
-                    link = hl ? ll : lr;
+                if (hl || hr) {
+                    // near child first; ties go left (bvh.h:216-219)
+                    const bool right_first = hr && (!hl || dl > dr);
+                    link = right_first ? lr : ll;
+                    if (hl && hr) {  // local-memory stores cost L1 wavefronts: only when there is a far child
+                        stack[sp] = make_float2(__int_as_float(right_first ? ll : lr), right_first ? dl : dr);
+                        ++sp;
+                    }
                 } else {
                     pop();
                 }
@@ -225,14 +247,22 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
             while (__any_sync(FULL, more)) {
                 if (more) {
                     const char *p = reinterpret_cast<const char *>(bvh.tris + k);
-                    const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
-                    float t, b, c;
-                    if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, eps, t, b, c) &&
-                        t < best.t) {
-                        best.t = t;
-                        best.b = b;
-                        best.c = c;
-                        best.tri = static_cast<int32_t>(k);
+                    const f8 ta = ld8(p);
+                    const f4 t2 = ld4(p + 32);
+                    const f4 t0 = f4{ta.a, ta.b, ta.c, ta.d}, t1 = f4{ta.e, ta.f, ta.g, ta.h};
+                    // intersect_ray_triangle, bvh.h:36-65 (same expression as tri_test() in pt_core.cuh with
+                    // a correctly rounded reciprocal instead of the division)
+                    const f3 e1 = mk3(t1.x, t1.y, t1.z), e2 = mk3(t2.x, t2.y, t2.z);
+                    const f3 n = cross(e1, e2);
+                    const f3 y = o - mk3(t0.x, t0.y, t0.z);
+                    const f3 r = cross(d, y);
+                    const float inv = rcp_rn(-dot(d, n));
+                    const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
+                    if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < best_t) {
+                        best_t = t;
+                        best_b = beta;
+                        best_c = gamma;
+                        best_tri = static_cast<int32_t>(k);
                     }
                     more = !(f2u(t0.w) & RT_LAST_BIT);
                     ++k;
@@ -248,6 +278,70 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(q.stats + 0, static_cast<unsigned long long>(count));
 }
 
+// bvh_mix_dist::pdf (raytracer.h:363-375) for all 32 lanes as one warp-synchronous loop: every iteration
+// a lane either takes one inner-node step of the light BVH or tests one triangle (a leaf in progress is
+// carried as the link ~next_triangle), and the loop ends on a warp vote.  The per-thread light_pdf() of
+// pt_core.cuh ran with 2-5 of 32 lanes active inside k_shade; this keeps the lanes converged.
+__device__ __forceinline__ float light_pdf_warp(const DScene &s, bool active, f3 x, f3 dir) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const DBvh &bvh = s.light;
+    int32_t stack[RT_STACK_SIZE];
+    int sp = 0;
+    int32_t link = (active && bvh.root != RT_LINK_NONE) ? bvh.root : kLinkDone;
+    const f3 idir = mk3(rcp_rn(dir.x), rcp_rn(dir.y), rcp_rn(dir.z));
+    const f3 ood = mk3(x.x * idir.x, x.y * idir.y, x.z * idir.z);
+    float sum = 0.0f;
+    while (__any_sync(FULL, link != kLinkDone)) {
+        if (link >= 0) {
+            const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
+            const f8 na = ld8(p), nb = ld8(p + 32);
+            const float lx0 = fmaf(na.a, idir.x, -ood.x), lx1 = fmaf(na.d, idir.x, -ood.x);
+            const float ly0 = fmaf(na.b, idir.y, -ood.y), ly1 = fmaf(na.e, idir.y, -ood.y);
+            const float lz0 = fmaf(na.c, idir.z, -ood.z), lz1 = fmaf(na.f, idir.z, -ood.z);
+            const float rx0 = fmaf(na.g, idir.x, -ood.x), rx1 = fmaf(nb.b, idir.x, -ood.x);
+            const float ry0 = fmaf(na.h, idir.y, -ood.y), ry1 = fmaf(nb.c, idir.y, -ood.y);
+            const float rz0 = fmaf(nb.a, idir.z, -ood.z), rz1 = fmaf(nb.d, idir.z, -ood.z);
+            // all-hit traversal: a box is entered iff t_min <= t_max && t_max >= eps (bvh.h:147), no upper bound
+            const bool hl = fmaxf(fmax3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), s.eps) <=
+                            fmin3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1));
+            const bool hr = fmaxf(fmax3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), s.eps) <=
+                            fmin3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1));
+            const int32_t ll = static_cast<int32_t>(f2u(nb.e)), lr = static_cast<int32_t>(f2u(nb.f));
+            if (hl && hr) {
+                stack[sp++] = lr;
+                link = ll;
+            } else if (hl || hr) {
+                link = hl ? ll : lr;
+            } else {
+                link = sp > 0 ? stack[--sp] : kLinkDone;
+            }
+        } else if (link != kLinkDone) {
+            const uint32_t k = static_cast<uint32_t>(~link);
+            const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+            const f8 ta = ld8(p);
+            const f4 t2 = ld4(p + 32);
+            const f3 e1 = mk3(ta.e, ta.f, ta.g), e2 = mk3(t2.x, t2.y, t2.z);
+            const f3 n = cross(e1, e2);
+            const f3 y = x - mk3(ta.a, ta.b, ta.c);
+            const f3 r = cross(dir, y);
+            const float inv = rcp_rn(-dot(dir, n));
+            const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
+            if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= s.eps) {
+                const f4 le = ld4(s.light_extra + k);
+                const f3 xy = dir * t;  // y - x
+                const float d2 = len2(xy);
+                const f3 w = xy * rsqrtf(d2);
+                sum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);  // raytracer.h:79-84,255-261
+            }
+            if (f2u(ta.d) & RT_LAST_BIT)
+                link = sp > 0 ? stack[--sp] : kLinkDone;
+            else
+                link = ~static_cast<int32_t>(k + 1);  // next triangle of the same leaf
+        }
+    }
+    return sum / static_cast<float>(s.n_lights);
+}
+
 __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q,
                                                         uint32_t bounce) {
     __shared__ float lut[256];
@@ -261,8 +355,11 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene s, const float *
         const uint32_t i = warp_fetch(q.fetch_shade + bounce);
         if (i - lane_id() >= count) break;
         bool alive = false;
-        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(0, 0, 0);
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(0, 0, 0), rad = mk3(0, 0, 0);
         uint32_t pixel = 0, sample = 0;
+        ShadeMid mid;
+        mid.pos = mid.dir = mk3(0, 0, 1);
+        ShadeStep step = SHADE_END;
         if (i < count) {
             const float4 o4 = q.o[in][i], d4 = q.d[in][i], t4 = q.thr[in][i], h4 = q.hit[i];
             o = mk3(o4.x, o4.y, o4.z);
@@ -276,17 +373,24 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(DScene s, const float *
             h.c = h4.z;
             h.tri = __float_as_int(h4.w);
             const RngKey key{pixel, sample, bp.k0, bp.k1};
-            f3 rad = mk3(0, 0, 0);
             n_shade += h.tri >= 0 ? 1u : 0u;
-            alive = shade_bounce(s, lut, key, bounce, last, h, o, d, thr, rad, n_light);
-            if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f) {  // NaN != 0 is true: poisons the sample like the reference
-                const uint32_t slot = (sample - bp.s0) * bp.npix + (pixel - bp.pix0);
-                float4 acc = q.rad[slot];
-                acc.x += rad.x;
-                acc.y += rad.y;
-                acc.z += rad.z;
-                q.rad[slot] = acc;
-            }
+            step = shade_begin(s, lut, key, bounce, last, h, o, d, thr, rad, mid);
+            alive = step == SHADE_PASS;
+        }
+        // light pdf of every sampled direction, lanes converged (skipped entirely for scenes without lights)
+        float p_light = 0.0f;
+        if (s.n_lights > 0) {
+            p_light = light_pdf_warp(s, step == SHADE_SAMPLED, mid.pos, mid.dir);
+            n_light += step == SHADE_SAMPLED ? 1u : 0u;
+        }
+        if (step == SHADE_SAMPLED) alive = shade_finish(s, mid, p_light, o, d, thr);
+        if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f) {  // NaN != 0 is true: poisons the sample like the reference
+            const uint32_t slot = (sample - bp.s0) * bp.npix + (pixel - bp.pix0);
+            float4 acc = q.rad[slot];
+            acc.x += rad.x;
+            acc.y += rad.y;
+            acc.z += rad.z;
+            q.rad[slot] = acc;
         }
         const uint32_t dst = warp_append(q.count + bounce + 1, alive);
         if (alive) {

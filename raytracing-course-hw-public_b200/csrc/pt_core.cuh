@@ -60,6 +60,24 @@ RT_HD f4 ld4(const void *p) { return *reinterpret_cast<const f4 *>(p); }
 RT_HD uint32_t ldu(const uint32_t *p) { return *p; }
 #endif
 
+// 256-bit read-only load (LDG.E.256 on sm_100a; needs a 32-byte aligned address): one L1 tag lookup per
+// lane instead of two.  The traversal is bound by L1TEX wavefronts (one per distinct 128 B line per load
+// instruction), so halving the number of load instructions per node is what matters.
+struct alignas(32) f8 {
+    float a, b, c, d, e, f, g, h;
+};
+#if defined(__CUDA_ARCH__)
+RT_HD f8 ld8(const void *p) {
+    f8 v;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v.a), "=f"(v.b), "=f"(v.c), "=f"(v.d), "=f"(v.e), "=f"(v.f), "=f"(v.g), "=f"(v.h)
+        : "l"(p));
+    return v;
+}
+#else
+RT_HD f8 ld8(const void *p) { return *reinterpret_cast<const f8 *>(p); }
+#endif
+
 RT_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)
     return __float_as_uint(f);
@@ -191,7 +209,9 @@ RT_HD Hit closest_hit(const DBvh &bvh, f3 o, f3 d, float min_dst) {
     for (;;) {
         if (link >= 0) {
             const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
-            const f4 n0 = ld4(p), n1 = ld4(p + 16), n2 = ld4(p + 32), n3 = ld4(p + 48);
+            const f8 na = ld8(p), nb = ld8(p + 32);
+            const f4 n0 = f4{na.a, na.b, na.c, na.d}, n1 = f4{na.e, na.f, na.g, na.h};
+            const f4 n2 = f4{nb.a, nb.b, nb.c, nb.d}, n3 = f4{nb.e, nb.f, nb.g, nb.h};
             const float dl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, idir, min_dst);
             const float dr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, idir, min_dst);
             const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
@@ -252,7 +272,9 @@ RT_HD float light_pdf(const DScene &s, f3 x, f3 dir) {
     for (;;) {
         if (link >= 0) {
             const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
-            const f4 n0 = ld4(p), n1 = ld4(p + 16), n2 = ld4(p + 32), n3 = ld4(p + 48);
+            const f8 na = ld8(p), nb = ld8(p + 32);
+            const f4 n0 = f4{na.a, na.b, na.c, na.d}, n1 = f4{na.e, na.f, na.g, na.h};
+            const f4 n2 = f4{nb.a, nb.b, nb.c, nb.d}, n3 = f4{nb.e, nb.f, nb.g, nb.h};
             const bool hl = slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, x, idir, s.eps) >= 0.0f;
             const bool hr = slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, x, idir, s.eps) >= 0.0f;
             const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
@@ -350,7 +372,9 @@ RT_HD Surface make_surface(const DScene &s, const float *lut, const Hit &h, f3 d
     const char *tp = reinterpret_cast<const char *>(s.scene.tris + h.tri);
     const f4 t1 = ld4(tp + 16), t2 = ld4(tp + 32);
     const char *ap = reinterpret_cast<const char *>(s.attrs + h.tri);
-    const f4 a0 = ld4(ap), a1 = ld4(ap + 16), a2 = ld4(ap + 32), a3 = ld4(ap + 48);
+    const f8 aa = ld8(ap), ab = ld8(ap + 32);
+    const f4 a0 = f4{aa.a, aa.b, aa.c, aa.d}, a1 = f4{aa.e, aa.f, aa.g, aa.h};
+    const f4 a2 = f4{ab.a, ab.b, ab.c, ab.d}, a3 = f4{ab.e, ab.f, ab.g, ab.h};
     f3 ng = normalize(cross(mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z)));  // Object::base_normal
     const bool inside = dot(ng, dir) > 0.0f;                                   // bvh.h:92
     const float w0 = 1.0f - h.b - h.c;                                         // triangle::interop, geometry.h:497-502
@@ -359,7 +383,9 @@ RT_HD Surface make_surface(const DScene &s, const float *lut, const Hit &h, f3 d
     const float tu = a0.w * w0 + a2.w * h.b + a3.y * h.c;
     const float tv = a1.w * w0 + a3.x * h.b + a3.z * h.c;
     const char *mp = reinterpret_cast<const char *>(s.materials + f2u(a3.w));
-    const f4 m0 = ld4(mp), m1 = ld4(mp + 16), m2 = ld4(mp + 32), m3 = ld4(mp + 48);
+    const f8 ma = ld8(mp), mb = ld8(mp + 32);
+    const f4 m0 = f4{ma.a, ma.b, ma.c, ma.d}, m1 = f4{ma.e, ma.f, ma.g, ma.h};
+    const f4 m2 = f4{mb.a, mb.b, mb.c, mb.d}, m3 = f4{mb.e, mb.f, mb.g, mb.h};
     const int32_t color_tex = static_cast<int32_t>(f2u(m2.z)), emissive_tex = static_cast<int32_t>(f2u(m2.w));
     const int32_t mr_tex = static_cast<int32_t>(f2u(m3.x)), normal_tex = static_cast<int32_t>(f2u(m3.y));
 
@@ -538,47 +564,76 @@ RT_HD f3 pbr_brdf(const Surface &sf, float alpha, f3 in_dir, f3 out_dir) {
 //   throughput *= scl  (raytracer.h:580-590)
 // Returns true when the path continues with (o, d).
 // ------------------------------------------------------------------------------------------------
-RT_HD bool shade_bounce(const DScene &s, const float *lut, const RngKey &key, uint32_t bounce, bool last_bounce,
-                        const Hit &h, f3 &o, f3 &d, f3 &thr, f3 &radiance, uint32_t &light_rays) {
+// The bounce is split in two so that the kernel can run the light-pdf traversal of all 32 lanes as ONE
+// warp-synchronous loop between the halves (k_shade); shade_bounce() below is the plain composition.
+struct ShadeMid {
+    Surface sf;
+    f3 pos, dir;
+    float alpha;
+};
+enum ShadeStep { SHADE_END = 0, SHADE_PASS = 1, SHADE_SAMPLED = 2 };
+
+// First half: miss / hit data / alpha coin / emission / direction sampling (raytracer.h:555-571).
+//   SHADE_END     path finished (radiance updated)
+//   SHADE_PASS    alpha pass-through: continue from `o` (updated) along the same `d`
+//   SHADE_SAMPLED a direction was sampled; call shade_finish with the light pdf of (mid.pos, mid.dir)
+RT_HD ShadeStep shade_begin(const DScene &s, const float *lut, const RngKey &key, uint32_t bounce, bool last_bounce,
+                            const Hit &h, f3 &o, const f3 &d, const f3 &thr, f3 &radiance, ShadeMid &mid) {
     if (h.tri < 0) {  // miss: Scene::bg_at with the constant white environment, scene.h:83-89
         radiance = radiance + thr * mk3(s.bg[0], s.bg[1], s.bg[2]);
-        return false;
+        return SHADE_END;
     }
-    const Surface sf = make_surface(s, lut, h, d);
-    const f3 pos = o + d * h.t;  // ray.at(t): the next ray starts exactly here, no normal offset
+    mid.sf = make_surface(s, lut, h, d);
+    mid.pos = o + d * h.t;  // ray.at(t): the next ray starts exactly here, no normal offset
     const u4 r0 = rng_block(key, bounce, 0);
-    if (!(u01(r0.x) <= sf.alpha)) {  // alpha pass-through consumes a bounce, drops this hit's emission (raytracer.h:559-561)
-        o = pos;
-        return !last_bounce;
+    if (!(u01(r0.x) <= mid.sf.alpha)) {  // alpha pass-through consumes a bounce, drops this hit's emission (raytracer.h:559-561)
+        o = mid.pos;
+        return last_bounce ? SHADE_END : SHADE_PASS;
     }
-    radiance = radiance + thr * sf.emission;  // every remaining exit of shade() returns emission (+ ...)
-    if (last_bounce) return false;            // trace_ray(depth 0) = 0, raytracer.h:596-598
-    const float rough = fmaxf(sf.roughness, s.min_roughness);
-    const float alpha = rough * rough;
-    f3 dir;
+    radiance = radiance + thr * mid.sf.emission;  // every remaining exit of shade() returns emission (+ ...)
+    if (last_bounce) return SHADE_END;            // trace_ray(depth 0) = 0, raytracer.h:596-598
+    const float rough = fmaxf(mid.sf.roughness, s.min_roughness);
+    mid.alpha = rough * rough;
     if (u01(r0.y) <= s.vndf_factor) {
-        dir = vndf_sample(alpha, d, sf.ns, u01(r0.z), u01(r0.w));
+        mid.dir = vndf_sample(mid.alpha, d, mid.sf.ns, u01(r0.z), u01(r0.w));
     } else {
         const u4 r1 = rng_block(key, bounce, 1);
         // mix_dist{cosine, bvh_mix}: uniform selector, raytracer.h:383-392; cosine only without lights (:449-453)
         const bool pick_light = s.n_lights > 0 && !(u01(r0.z) * 2.0f < 1.0f);
-        dir = pick_light ? light_sample(s, pos, u01(r0.w), u01(r1.x), u01(r1.y)) : cosine_sample(sf.ng, u01(r1.x), u01(r1.y));
+        mid.dir = pick_light ? light_sample(s, mid.pos, u01(r0.w), u01(r1.x), u01(r1.y))
+                             : cosine_sample(mid.sf.ng, u01(r1.x), u01(r1.y));
     }
-    if (any_nan(dir)) return false;  // raytracer.h:569-571
-    const float p_vndf = vndf_pdf(alpha, s.eps, d, sf.ns, dir);
-    float p_mis = cosine_pdf(sf.ng, dir);
-    if (s.n_lights > 0) {  // mix_dist::pdf = mean of the sub-pdfs, raytracer.h:395-407
-        p_mis = (p_mis + light_pdf(s, pos, dir)) * 0.5f;
-        ++light_rays;
-    }
+    if (any_nan(mid.dir)) return SHADE_END;  // raytracer.h:569-571
+    return SHADE_SAMPLED;
+}
+
+// Second half: pdf mixture, BRDF, throughput (raytracer.h:572-590). `p_light` = bvh_mix_dist::pdf of
+// (mid.pos, mid.dir), ignored when the scene has no lights. Returns true when the path continues.
+RT_HD bool shade_finish(const DScene &s, const ShadeMid &mid, float p_light, f3 &o, f3 &d, f3 &thr) {
+    const float p_vndf = vndf_pdf(mid.alpha, s.eps, d, mid.sf.ns, mid.dir);
+    float p_mis = cosine_pdf(mid.sf.ng, mid.dir);
+    if (s.n_lights > 0) p_mis = (p_mis + p_light) * 0.5f;  // mix_dist::pdf = mean of the sub-pdfs, raytracer.h:395-407
     const float p = s.vndf_factor * p_vndf + (1.0f - s.vndf_factor) * p_mis;
     if (p < s.eps) return false;  // raytracer.h:576-578 (NaN p continues, like the reference)
-    const f3 scl = pbr_brdf(sf, alpha, d, dir) * (fmaxf(0.0f, dot(dir, sf.ns)) / p);
+    const f3 scl = pbr_brdf(mid.sf, mid.alpha, d, mid.dir) * (fmaxf(0.0f, dot(mid.dir, mid.sf.ns)) / p);
     if (len2(scl) == 0.0f) return false;  // raytracer.h:584-586
     thr = thr * scl;
-    o = pos;
-    d = dir;
+    o = mid.pos;
+    d = mid.dir;
     return true;
+}
+
+RT_HD bool shade_bounce(const DScene &s, const float *lut, const RngKey &key, uint32_t bounce, bool last_bounce,
+                        const Hit &h, f3 &o, f3 &d, f3 &thr, f3 &radiance, uint32_t &light_rays) {
+    ShadeMid mid;
+    const ShadeStep step = shade_begin(s, lut, key, bounce, last_bounce, h, o, d, thr, radiance, mid);
+    if (step != SHADE_SAMPLED) return step == SHADE_PASS;
+    float p_light = 0.0f;
+    if (s.n_lights > 0) {
+        p_light = light_pdf(s, mid.pos, mid.dir);
+        ++light_rays;
+    }
+    return shade_finish(s, mid, p_light, o, d, thr);
 }
 
 // sanitize_nans, raytracer.h:607-616: per channel NaN -> 0, Inf kept

@@ -101,6 +101,7 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
         t.e1x = p[3] - p[0]; t.e1y = p[4] - p[1]; t.e1z = p[5] - p[2];
         t.e2x = p[6] - p[0]; t.e2y = p[7] - p[1]; t.e2z = p[8] - p[2];
         t.pad0 = t.pad1 = 0.0f;
+        t.pad2[0] = t.pad2[1] = t.pad2[2] = t.pad2[3] = 0.0f;
         t.id_last = id;
     }
     if (src.root == RT_NO_CHILD || src.n_objects == 0) return RT_OK;

@@ -7,7 +7,8 @@
 //   DNode  64 B  one per INNER node of the reference tree: both children's boxes + child links.
 //                The reference tests both child boxes at the parent (bvh.h:205-212), so one
 //                64 B fetch replaces two 40 B node fetches.
-//   DTri   48 B  triangle in BVH order: a, (b-a), (c-a) + scene.objects id + end-of-leaf flag.
+//   DTri   64 B  triangle in BVH order: a, (b-a), (c-a) + scene.objects id + end-of-leaf flag, padded to
+//                64 B so that it is two 256-bit loads (LDG.E.256 on sm_100a) inside one 128 B line.
 //   DAttr  64 B  per-vertex normals + uv + material id, BVH order (read once per shade).
 //   DMat   64 B  deduplicated material.
 //
@@ -22,7 +23,7 @@
 #define RT_LINK_NONE 0x7FFFFFFF /* empty BVH */
 #define RT_LAST_BIT 0x80000000u
 
-struct alignas(16) DNode {
+struct alignas(64) DNode {
     // lo/hi of the left (l) and right (r) child boxes
     float lminx, lminy, lminz, lmaxx;
     float lmaxy, lmaxz, rminx, rminy;
@@ -31,14 +32,15 @@ struct alignas(16) DNode {
     int32_t pad0, pad1;
 };
 
-struct alignas(16) DTri {
+struct alignas(64) DTri {
     float ax, ay, az;
     uint32_t id_last;  // scene.objects index | RT_LAST_BIT on the last triangle of a leaf
     float e1x, e1y, e1z, pad0;  // b - a  (triangle::v, geometry.h:473)
     float e2x, e2y, e2z, pad1;  // c - a  (triangle::u, geometry.h:475)
+    float pad2[4];
 };
 
-struct alignas(16) DAttr {
+struct alignas(64) DAttr {
     float n0x, n0y, n0z, uv0x;
     float n1x, n1y, n1z, uv0y;
     float n2x, n2y, n2z, uv1x;
@@ -52,7 +54,7 @@ struct alignas(16) DTangent {  // only when some tangent differs from (1,0,0)
     float t2z, pad0, pad1, pad2;
 };
 
-struct alignas(16) DMat {
+struct alignas(64) DMat {
     float color[4];
     float emission[3];
     float roughness;
