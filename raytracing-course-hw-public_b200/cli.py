@@ -1,0 +1,40 @@
+"""`python -m rt_b200.cli <scene.gltf> <width> <height> <samples> <out.ppm>` — the reference's CLI surface
+(src/main.cpp:16-49) for hosts without the reference headers: Python loader (gltf.py, bit-identical flattening),
+own BVH build (librt_host), CUDA integrator (librt_gpu), reference tonemap restated in librt_host, binary PPM."""
+import os
+import sys
+
+
+def run_raytracer(scene, width, height, samples, seed=0, n_gpus=1):
+    """Mirror of run_raytracer(scene, image) (src/raytracer.h:629): float means [H, W, 3] + stats."""
+    from . import gpu
+
+    with gpu.RtGpu(n_gpus, 0) as rt:
+        rt.upload_scene(scene)
+        rt.render(width, height, samples, seed=seed)
+        return rt.readback()
+
+
+def main(argv=None):
+    argv = sys.argv if argv is None else argv
+    if len(argv) < 6:
+        print(f"Too few arguments: expected 6, got {len(argv) - 1}", file=sys.stderr)
+        return 1
+    from . import gltf, host
+
+    try:
+        width, height, samples = int(argv[2]), int(argv[3]), int(argv[4])
+        scene = gltf.load_gltf(argv[1], width / height)
+        mean, stats = run_raytracer(scene, width, height, samples, seed=int(os.environ.get("RT_SEED", "0")),
+                                    n_gpus=int(os.environ.get("RT_GPUS", "1")))
+        host.write_ppm(argv[5], host.tonemap_rgb8(mean))
+        ms = max(stats["render_ms"], 1e-9)
+        print(f"rt_gpu: {ms:.1f} ms, {stats['samples'] / ms * 1e-3:.1f} Msamples/s", file=sys.stderr)
+    except RuntimeError as e:
+        print(e, file=sys.stderr)
+        return 1
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

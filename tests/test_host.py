@@ -183,3 +183,34 @@ def test_device_math_follows_oracle_paths(name, tol_frac, hc, manifest, golden_s
     assert (rel > 1e-3).mean() <= tol_frac
     assert abs(np.mean(out) - np.mean(ref)) < 2e-3 * np.mean(ref)
     assert abs(cnt[0] - st["extension_rays"]) <= 0.02 * st["extension_rays"]
+
+
+# ---- CLI surface (src/main.cpp:16-49) ---------------------------------------------------------------------
+CLI = os.path.join(ROOT, "bin", "raytracer_b200")
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="reference-hosted CLI not built (reference sources absent)")
+def test_cli_argument_errors_match_reference():
+    import subprocess
+
+    r = subprocess.run([CLI, "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Too few arguments: expected 6, got 2" in r.stderr
+    if os.path.exists(O.REF_BINARY):
+        q = subprocess.run([O.REF_BINARY, "a", "b"], capture_output=True, text=True)
+        assert (q.returncode, q.stderr) == (r.returncode, r.stderr)
+
+
+@pytest.mark.skipif(not os.path.exists(CLI) or __import__("torch").cuda.is_available(), reason="CPU-only behaviour")
+def test_cli_fails_loudly_without_gpu(scene_dir, tmp_path):
+    import subprocess
+
+    r = subprocess.run([CLI, scene_dir("tiny"), "16", "12", "2", str(tmp_path / "o.ppm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "rt_gpu_create failed (-2)" in r.stderr
+    assert not (tmp_path / "o.ppm").exists()
+
+
+def test_python_cli_argument_error(capsys):
+    from rt_b200 import cli
+
+    assert cli.main(["prog", "x"]) == 1
+    assert "Too few arguments: expected 6, got 1" in capsys.readouterr().err
