@@ -99,16 +99,40 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
 //   * every loop condition is a warp vote (__any_sync / __ballot_sync), so the 32 lanes re-converge at
 //     each phase boundary instead of drifting apart (the naive per-thread loop ran its triangle tests
 //     with 2 of 32 lanes active);
-//   * inner phase: lanes descend inner nodes; the first leaf a lane meets is postponed and the lane keeps
-//     descending speculatively; a lane that meets a second leaf waits.  The phase ends when no lane is
-//     still looking for its first leaf;
+//   * inner phase: one iteration = at most one stack pop, then at most one node step per lane, all
+//     predicated (no per-lane loops: the pop-until-useful loop of the first version ran with 2 of 32 lanes
+//     active and was 9 % of the kernel's instructions).  The first leaf a lane meets is postponed and the
+//     lane keeps descending speculatively; a lane that meets a second leaf waits.  The phase ends when fewer
+//     than kMinSearching lanes are still looking for their first leaf;
 //   * leaf phase: all postponed leaves are intersected together, triangle by triangle;
 //   * a lane whose ray is finished stores its hit and takes the next ray from a warp-local block of
 //     kRayBlock queue entries (one atomicAdd per block), ranks handed out with __ballot_sync/__popc.
 // Visiting order (near child first, ties left first, bvh.h:216) and strictly-closer-wins (bvh.h:132)
 // are those of closest_hit() in pt_core.cuh, so both give the same hit.
-constexpr int32_t kLinkDone = static_cast<int32_t>(0x80000000u);
+//
+// Compile-time knobs (A/B-tested on the B200, DESIGN.md "k_extend"; defaults = the fastest measured):
+#ifndef RT_EXT_QNODE
+#define RT_EXT_QNODE 1        // 1: 32-byte quantised nodes (one sector per visit)  0: 64-byte full-precision DNodes
+#endif
+#ifndef RT_EXT_SMEM_STACK
+#define RT_EXT_SMEM_STACK 16  // traversal-stack entries per thread kept in shared memory (0: all in local memory)
+#endif
+#ifndef RT_EXT_POP_LOOP
+#define RT_EXT_POP_LOOP 0     // 1: a lane pops until it finds a useful entry (divergent loop)  0: one pop per iteration
+#endif
+#ifndef RT_EXT_MIN_SEARCH
+#define RT_EXT_MIN_SEARCH 16  // leave the inner phase when fewer lanes than this still look for their first leaf
+#endif
+constexpr int32_t kLinkDone = static_cast<int32_t>(0x80000000u);  // nothing left to traverse
+constexpr int32_t kLinkPop = static_cast<int32_t>(0x80000001u);   // take the next entry from the stack
 constexpr uint32_t kRayBlock = 128;
+// Traversal stack: the first kSmemStack entries of every thread live in shared memory ([entry][thread], so
+// a warp's access is bank-conflict free whatever the lanes' stack pointers are); deeper entries (rare: the
+// ordered traversal seldom holds more than a dozen postponed children) overflow to local memory.  The
+// all-local stack cost one 32 B sector of L1 data-pipe time per lane and push (write-through to L2: 4.2 GB
+// per launch, 31 % of the kernel's L1 sectors — profiles/r1_v2_k_extend_ncu_full.csv).
+constexpr int kSmemStack = RT_EXT_SMEM_STACK;
+constexpr int kMinSearching = RT_EXT_MIN_SEARCH;
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
 // MUFU.RCP (1 ulp): one instruction instead of the IEEE division's Newton step + slow path
@@ -120,6 +144,8 @@ __device__ __forceinline__ float rcp_rn(float x) {
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+__device__ __forceinline__ bool link_is_leaf(int32_t link) { return link < 0 && link != kLinkDone && link != kLinkPop; }
+
 __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, Queues q, uint32_t bounce) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
@@ -129,9 +155,13 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    float2 stack[RT_STACK_SIZE];  // (link bits, entry distance) of postponed far children
+    // postponed far children: link and entry distance
+    __shared__ int32_t s_link[kSmemStack > 0 ? kSmemStack : 1][kExtendThreads];
+    __shared__ float s_dist[kSmemStack > 0 ? kSmemStack : 1][kExtendThreads];
+    float2 overflow[RT_STACK_SIZE - kSmemStack];
+    const uint32_t tid = threadIdx.x;
     int sp = 0;
-    int32_t link = kLinkDone;  // >= 0 inner node, < 0 leaf (~first triangle), kLinkDone = nothing left
+    int32_t link = kLinkDone;  // >= 0 inner node, kLinkPop / kLinkDone, otherwise a leaf (~first triangle)
     int32_t leaf = 0;          // postponed leaf link (always < 0) or 0 = none
     uint32_t ray = kNoRay;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1), ood = mk3(0, 0, 0);
@@ -139,18 +169,6 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
     int32_t best_tri = -1;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
-
-    auto pop = [&]() {
-        link = kLinkDone;
-        while (sp > 0) {
-            --sp;
-            const float2 e = stack[sp];
-            if (e.y < best_t) {  // bvh.h:221: the far child is visited only while best is farther
-                link = __float_as_int(e.x);
-                break;
-            }
-        }
-    };
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes ---------------------------------------------------
@@ -187,56 +205,95 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
                 best_b = best_c = 0.0f;
                 best_tri = -1;
                 sp = 0;
-                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
-                if (link < 0 && link != kLinkDone) {  // the root itself is a leaf
-                    leaf = link;
-                    link = kLinkDone;
-                }
+                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;  // a leaf root is postponed below
             }
             pool_next += take;
             if (avail == 0 && m_idle == FULL) break;  // queue drained and nothing in flight
         }
+        const bool can_refill = !exhausted || pool_next != pool_end;  // warp-uniform
 
         // ---- inner phase -------------------------------------------------------------------------------
         for (;;) {
-            const bool searching = link >= 0 && leaf == 0;
-            if (!__any_sync(FULL, searching)) break;
+            // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
+            //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)
+#if RT_EXT_POP_LOOP
+            while (link == kLinkPop) {
+#else
+            if (link == kLinkPop) {
+#endif
+                if (sp == 0) {
+                    link = kLinkDone;
+                } else {
+                    --sp;
+                    int32_t l;
+                    float t;
+                    if (kSmemStack > 0 && sp < kSmemStack) {
+                        l = s_link[sp][tid];
+                        t = s_dist[sp][tid];
+                    } else {
+                        const float2 e = overflow[sp - kSmemStack];
+                        l = __float_as_int(e.x);
+                        t = e.y;
+                    }
+                    link = t < best_t ? l : kLinkPop;
+                }
+            }
+            // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
+            if (leaf == 0 && link_is_leaf(link)) {
+                leaf = link;
+                link = kLinkPop;
+            }
+            // (3) phase vote
+            const bool searching = leaf == 0 && link != kLinkDone;
+            const uint32_t m_search = __ballot_sync(FULL, searching);
+            if (m_search == 0) break;
+            if (kMinSearching > 1 && __popc(m_search) < kMinSearching) {
+                // few lanes still search: go and do useful work for the others if there is any (pending
+                // leaves to intersect, or finished lanes that can take a new ray); else keep going
+                const bool other_work = leaf != 0 || (can_refill && link == kLinkDone);
+                if (__any_sync(FULL, other_work)) break;
+            }
+            // (4) at most one node step
             if (link >= 0) {
+#if RT_EXT_QNODE
+                const f8 nq = ld8(bvh.qnodes + link);  // 32 B quantised node = one sector, one 256-bit load
+                const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood,
+                                               eps, best_t);
+                const bool hl = nt.hl, hr = nt.hr;
+                const float dl = nt.dl, dr = nt.dr;
+                const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
+#else
                 const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
                 const f8 na = ld8(p), nb = ld8(p + 32);  // 64 B node = two 256-bit loads
-                const f4 n0 = f4{na.a, na.b, na.c, na.d}, n1 = f4{na.e, na.f, na.g, na.h};
-                const f4 n2 = f4{nb.a, nb.b, nb.c, nb.d}, n3 = f4{nb.e, nb.f, nb.g, nb.h};
                 // slab test of both children (bvh.h:137-152) in fused form t = plane * (1/d) - o/d; the
-                // interval is clipped to [eps, best_t] inside the min/max chain (hit <=> lo <= hi), which
-                // visits exactly the boxes `t_min <= t_max && t_max >= eps && max(t_min, eps) < best` does,
-                // plus harmless ties with best_t.
-                const float lx0 = fmaf(n0.x, idir.x, -ood.x), lx1 = fmaf(n0.w, idir.x, -ood.x);
-                const float ly0 = fmaf(n0.y, idir.y, -ood.y), ly1 = fmaf(n1.x, idir.y, -ood.y);
-                const float lz0 = fmaf(n0.z, idir.z, -ood.z), lz1 = fmaf(n1.y, idir.z, -ood.z);
-                const float rx0 = fmaf(n1.z, idir.x, -ood.x), rx1 = fmaf(n2.y, idir.x, -ood.x);
-                const float ry0 = fmaf(n1.w, idir.y, -ood.y), ry1 = fmaf(n2.z, idir.y, -ood.y);
-                const float rz0 = fmaf(n2.x, idir.z, -ood.z), rz1 = fmaf(n2.w, idir.z, -ood.z);
+                // interval is clipped to [eps, best_t] inside the min/max chain (hit <=> lo <= hi)
+                const float lx0 = fmaf(na.a, idir.x, -ood.x), lx1 = fmaf(na.d, idir.x, -ood.x);
+                const float ly0 = fmaf(na.b, idir.y, -ood.y), ly1 = fmaf(na.e, idir.y, -ood.y);
+                const float lz0 = fmaf(na.c, idir.z, -ood.z), lz1 = fmaf(na.f, idir.z, -ood.z);
+                const float rx0 = fmaf(na.g, idir.x, -ood.x), rx1 = fmaf(nb.b, idir.x, -ood.x);
+                const float ry0 = fmaf(na.h, idir.y, -ood.y), ry1 = fmaf(nb.c, idir.y, -ood.y);
+                const float rz0 = fmaf(nb.a, idir.z, -ood.z), rz1 = fmaf(nb.d, idir.z, -ood.z);
                 const float dl = fmaxf(fmax3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), eps);
                 const float el = fminf(fmin3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1)), best_t);
                 const float dr = fmaxf(fmax3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), eps);
                 const float er = fminf(fmin3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1)), best_t);
                 const bool hl = dl <= el, hr = dr <= er;
-                const int32_t ll = static_cast<int32_t>(f2u(n3.x)), lr = static_cast<int32_t>(f2u(n3.y));
-                if (hl || hr) {
-                    // near child first; ties go left (bvh.h:216-219)
-                    const bool right_first = hr && (!hl || dl > dr);
-                    link = right_first ? lr : ll;
-                    if (hl && hr) {  // local-memory stores cost L1 wavefronts: only when there is a far child
-                        stack[sp] = make_float2(__int_as_float(right_first ? ll : lr), right_first ? dl : dr);
-                        ++sp;
+                const int32_t ll = static_cast<int32_t>(f2u(nb.e)), lr = static_cast<int32_t>(f2u(nb.f));
+#endif
+                // near child first; ties go left (bvh.h:216-219)
+                const bool right_first = hr && (!hl || dl > dr);
+                if (hl && hr) {
+                    const int32_t far_link = right_first ? ll : lr;
+                    const float far_t = right_first ? dl : dr;
+                    if (kSmemStack > 0 && sp < kSmemStack) {
+                        s_link[sp][tid] = far_link;
+                        s_dist[sp][tid] = far_t;
+                    } else {
+                        overflow[sp - kSmemStack] = make_float2(__int_as_float(far_link), far_t);
                     }
-                } else {
-                    pop();
+                    ++sp;
                 }
-                if (link < 0 && link != kLinkDone && leaf == 0) {  // postpone the first leaf, keep descending
-                    leaf = link;
-                    pop();
-                }
+                link = (hl || hr) ? (right_first ? lr : ll) : kLinkPop;
             }
         }
 
@@ -268,11 +325,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, 
                     ++k;
                 }
             }
-            leaf = 0;
-            if (link < 0 && link != kLinkDone) {  // a lane that was waiting with a second leaf
-                leaf = link;
-                pop();
-            }
+            leaf = 0;  // a lane that waited with a second leaf postpones it in step (2) of the next inner phase
         }
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(q.stats + 0, static_cast<unsigned long long>(count));

@@ -188,6 +188,105 @@ RT_HD bool tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float min_dst, float &t, flo
     return beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= min_dst;
 }
 
+// ---- quantised node (QNode, rt_types.h): both child slab tests from one 32-byte record --------------------
+// Plane byte q of a word -> the float 1 + q * 2^-15 (q placed in mantissa bits 8..15 by one PRMT), so that
+//   t(q) = (org + q * cell - o) / d = fma(1 + q * 2^-15, A, B)   with  A = 2^15 * cell / d,  B = (org - o) / d - A
+// costs one PRMT + one FFMA per plane and no integer->float conversion.  A is 128 x the node's extent in ray
+// space, so B carries an absolute rounding error of ~2^-9 cell; the packer keeps a 1/64-cell margin for it.
+template <int K> RT_HD float qplane(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (K << 4)));
+#else
+    return u2f(0x3F800000u | (((w >> (8 * K)) & 255u) << 8));
+#endif
+}
+
+struct NodeTest {
+    float dl, dr;  // entry distances (clipped to eps from below)
+    bool hl, hr;
+};
+
+RT_HD NodeTest qnode_test(const uint32_t ox, const uint32_t oy, const uint32_t oz, const uint32_t q0, const uint32_t q1,
+                          const uint32_t q2, f3 idir, f3 ood, float eps, float best_t) {
+    const float ax = u2f((ox << 23) + 0x07800000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
+    const float ay = u2f((oy << 23) + 0x07800000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
+    const float az = u2f((oz << 23) + 0x07800000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
+    const float lx0 = fmaf(qplane<0>(q0), ax, bx), ly0 = fmaf(qplane<1>(q0), ay, by), lz0 = fmaf(qplane<2>(q0), az, bz);
+    const float lx1 = fmaf(qplane<3>(q0), ax, bx), ly1 = fmaf(qplane<0>(q1), ay, by), lz1 = fmaf(qplane<1>(q1), az, bz);
+    const float rx0 = fmaf(qplane<2>(q1), ax, bx), ry0 = fmaf(qplane<3>(q1), ay, by), rz0 = fmaf(qplane<0>(q2), az, bz);
+    const float rx1 = fmaf(qplane<1>(q2), ax, bx), ry1 = fmaf(qplane<2>(q2), ay, by), rz1 = fmaf(qplane<3>(q2), az, bz);
+    // slab test of both children (bvh.h:137-152), interval clipped to [eps, best_t] inside the min/max chain
+    // (hit <=> lo <= hi): visits the boxes `t_min <= t_max && t_max >= eps && max(t_min, eps) < best` does,
+    // plus harmless ties with best_t.  fminf/fmaxf drop NaNs (ray parallel to a slab): conservative.
+    NodeTest r;
+    r.dl = fmaxf(fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fminf(lz0, lz1)), eps);
+    const float el = fminf(fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1)), best_t);
+    r.dr = fmaxf(fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fminf(rz0, rz1)), eps);
+    const float er = fminf(fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1)), best_t);
+    r.hl = r.dl <= el;
+    r.hr = r.dr <= er;
+    return r;
+}
+
+// closest_hit() over the quantised nodes, in the kernel's arithmetic (1/d once, fused o/d) — the sequential
+// statement of what k_extend computes per ray; the host tests compare its hits with closest_hit()'s.
+RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst) {
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0.0f;
+    best.tri = -1;
+    if (bvh.root == RT_LINK_NONE) return best;
+    const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    int32_t stack_link[RT_STACK_SIZE];
+    float stack_t[RT_STACK_SIZE];
+    int sp = 0;
+    int32_t link = bvh.root;
+    for (;;) {
+        if (link >= 0) {
+            const f8 nq = ld8(bvh.qnodes + link);
+            const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood,
+                                           min_dst, best.t);
+            const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
+            if (nt.hl || nt.hr) {
+                const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);
+                link = right_first ? lr : ll;
+                if (nt.hl && nt.hr) {
+                    stack_link[sp] = right_first ? ll : lr;
+                    stack_t[sp] = right_first ? nt.dl : nt.dr;
+                    ++sp;
+                }
+                continue;
+            }
+        } else {
+            uint32_t k = static_cast<uint32_t>(~link);
+            for (;;) {
+                const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+                const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+                float t, b, c;
+                if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, min_dst, t, b,
+                             c) &&
+                    t < best.t) {
+                    best.t = t;
+                    best.b = b;
+                    best.c = c;
+                    best.tri = static_cast<int32_t>(k);
+                }
+                if (f2u(t0.w) & RT_LAST_BIT) break;
+                ++k;
+            }
+        }
+        for (;;) {
+            if (sp == 0) return best;
+            --sp;
+            if (stack_t[sp] < best.t) {
+                link = stack_link[sp];
+                break;
+            }
+        }
+    }
+}
+
 struct TravCounters {
     uint32_t nodes, tris;
 };

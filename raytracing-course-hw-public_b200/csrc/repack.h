@@ -4,6 +4,7 @@
 #ifndef RT_REPACK_H
 #define RT_REPACK_H
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -16,6 +17,7 @@ namespace rt {
 
 struct PackedBvh {
     std::vector<DNode> nodes;
+    std::vector<QNode> qnodes;    // quantised copy of `nodes` (same indices), see quantize_nodes()
     std::vector<DTri> tris;       // BVH object order
     std::vector<uint32_t> order;  // BVH position -> scene.objects index
     int32_t root = RT_LINK_NONE;
@@ -45,12 +47,26 @@ inline void set_box(DNode &n, bool left, const float *lo, const float *hi) {
     }
 }
 
+inline bool subtree_empty(const rt_bvh_desc &src, uint32_t ref_id, uint32_t depth) {
+    if (ref_id == RT_NO_CHILD) return true;
+    if (depth > RT_STACK_SIZE) return false;  // malformed (cyclic) input: reported by pack_node's depth check
+    const rt_bvh_node &nd = src.nodes[ref_id];
+    if (nd.left_child == RT_NO_CHILD && nd.right_child == RT_NO_CHILD) return nd.obj_begin >= nd.obj_end;
+    return subtree_empty(src, nd.left_child, depth + 1) && subtree_empty(src, nd.right_child, depth + 1);
+}
+
 // Returns the link of reference node `ref_id` (inner index or ~first_tri), or RT_LINK_NONE for an
-// empty leaf.  `rc` collects structural errors.
+// empty subtree.  An inner node with one empty side (the reference builder never makes one) is replaced
+// by its other child, so every packed inner node has two non-empty children.  `rc` collects structural errors.
 inline int32_t pack_node(const rt_bvh_desc &src, uint32_t ref_id, PackedBvh &out, uint32_t depth, int &rc) {
     const rt_bvh_node &nd = src.nodes[ref_id];
     if (depth > out.max_depth) out.max_depth = depth;
     const bool has_children = nd.left_child != RT_NO_CHILD || nd.right_child != RT_NO_CHILD;
+    if (has_children && depth < RT_STACK_SIZE && nd.obj_begin >= nd.obj_end) {
+        const bool el = subtree_empty(src, nd.left_child, depth + 1), er = subtree_empty(src, nd.right_child, depth + 1);
+        if (el && er) return RT_LINK_NONE;
+        if (el || er) return pack_node(src, el ? nd.right_child : nd.left_child, out, depth + 1, rc);
+    }
     if (!has_children) {
         if (nd.obj_begin >= nd.obj_end) return RT_LINK_NONE;
         out.tris[nd.obj_end - 1].id_last |= RT_LAST_BIT;
@@ -85,6 +101,87 @@ inline int32_t pack_node(const rt_bvh_desc &src, uint32_t ref_id, PackedBvh &out
     return idx;
 }
 
+inline uint32_t fbits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+inline float bitsf(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// One axis of a QNode: grid word (origin bits | cell exponent) and the four plane bytes
+// (left lo, left hi, right lo, right hi).  Conservative in exact arithmetic with a margin of 1/64 cell
+// for the device's ray-space rounding (pt_core.cuh, qnode_axis()).  Returns false when the extent
+// cannot be represented (non-finite box).
+inline bool quantize_axis(const float lo[2], const float hi[2], uint32_t &word, uint8_t q[4]) {
+    const float mn = lo[0] < lo[1] ? lo[0] : lo[1];
+    const float mx = hi[0] > hi[1] ? hi[0] : hi[1];
+    if (!(std::isfinite(mn) && std::isfinite(mx)) || mx < mn) return false;
+    const double margin = 1.0 / 64.0;
+    const double ext = static_cast<double>(mx) - static_cast<double>(mn);
+    int e_first = 1;
+    if (ext > 0.0) e_first = std::max(1, std::ilogb(ext / 255.0) + 127 - 1);
+    for (int e = e_first; e <= 239; ++e) {  // smallest cell that covers the extent in 255 steps
+        const double cell = std::ldexp(1.0, e - 127);
+        const uint32_t eb = static_cast<uint32_t>(e);
+        // origin = the float whose bits are (23 high bits chosen here | bit 8 = 0 | e); it has to be
+        // <= mn - margin * cell.  Round that target down to a float, then down to the representable words.
+        const double target = static_cast<double>(mn) - margin * cell;
+        float tf = static_cast<float>(target);
+        if (static_cast<double>(tf) > target) tf = std::nextafterf(tf, -std::numeric_limits<float>::infinity());
+        uint32_t w;
+        if (tf > 0.0f) {
+            const uint32_t tb = fbits(tf);
+            w = (tb & ~0x1FFu) | eb;
+            if (w > tb) w = (tb & ~0x1FFu) >= 0x200u ? w - 0x200u : (0x80000000u | eb);
+        } else {  // negative (or zero): more magnitude = smaller value
+            const uint32_t tb = tf == 0.0f ? 0x80000000u : fbits(tf);
+            w = (tb & ~0x1FFu) | eb;
+            if (w < tb) w += 0x200u;
+        }
+        const double org = static_cast<double>(bitsf(w));
+        if (!std::isfinite(org) || !(org <= target)) continue;
+        const double top = (static_cast<double>(mx) - org) / cell + margin;
+        if (top > 255.0) continue;
+        word = w;
+        for (int c = 0; c < 2; ++c) {
+            double a = std::floor((static_cast<double>(lo[c]) - org) / cell - margin);
+            double z = std::ceil((static_cast<double>(hi[c]) - org) / cell + margin);
+            if (a < 0.0) a = 0.0;  // cannot happen: org <= mn - margin * cell
+            if (z > 255.0) z = 255.0;
+            q[2 * c] = static_cast<uint8_t>(a);
+            q[2 * c + 1] = static_cast<uint8_t>(z);
+        }
+        return true;
+    }
+    return false;
+}
+
+inline int quantize_nodes(const std::vector<DNode> &nodes, std::vector<QNode> &out) {
+    out.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const DNode &n = nodes[i];
+        const float lo[3][2] = {{n.lminx, n.rminx}, {n.lminy, n.rminy}, {n.lminz, n.rminz}};
+        const float hi[3][2] = {{n.lmaxx, n.rmaxx}, {n.lmaxy, n.rmaxy}, {n.lmaxz, n.rmaxz}};
+        uint8_t q[3][4];
+        QNode &o = out[i];
+        for (int a = 0; a < 3; ++a)
+            if (!quantize_axis(lo[a], hi[a], o.org[a], q[a])) return RT_ERR_BAD_SCENE;
+        // byte order = DNode's plane order: lminx lminy lminz lmaxx | lmaxy lmaxz rminx rminy | rminz rmaxx rmaxy rmaxz
+        const uint8_t b[12] = {q[0][0], q[1][0], q[2][0], q[0][1], q[1][1], q[2][1],
+                               q[0][2], q[1][2], q[2][2], q[0][3], q[1][3], q[2][3]};
+        for (int w = 0; w < 3; ++w)
+            o.q[w] = static_cast<uint32_t>(b[4 * w]) | static_cast<uint32_t>(b[4 * w + 1]) << 8 |
+                     static_cast<uint32_t>(b[4 * w + 2]) << 16 | static_cast<uint32_t>(b[4 * w + 3]) << 24;
+        o.left = n.left;
+        o.right = n.right;
+    }
+    return RT_OK;
+}
+
 }  // namespace detail
 
 inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &out) {
@@ -107,7 +204,8 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     if (src.root == RT_NO_CHILD || src.n_objects == 0) return RT_OK;
     int rc = RT_OK;
     out.root = detail::pack_node(src, src.root, out, 0, rc);
-    return rc;
+    if (rc) return rc;
+    return detail::quantize_nodes(out.nodes, out.qnodes);
 }
 
 inline int pack_scene(const rt_scene_desc &sc, PackedScene &out) {

@@ -102,7 +102,9 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
     // scene
-    DevBuf<DNode> nodes, lnodes;
+    DevBuf<QNode> qnodes;  // scene BVH, quantised (k_extend)
+    DevBuf<DNode> nodes;   // scene BVH, full precision (only in RT_EXT_QNODE=0 builds)
+    DevBuf<DNode> lnodes;  // light BVH, full precision (k_shade's light-pdf traversal)
     DevBuf<DTri> tris, ltris;
     DevBuf<DAttr> attrs;
     DevBuf<DTangent> tangents;
@@ -149,7 +151,11 @@ namespace {
 
 int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p) {
     CU_CHECK(cudaSetDevice(d.device));
+#if RT_EXT_QNODE
+    if (int rc = d.qnodes.upload(p.scene.qnodes, d.stream)) return rc;
+#else
     if (int rc = d.nodes.upload(p.scene.nodes, d.stream)) return rc;
+#endif
     if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
     if (int rc = d.lnodes.upload(p.light.nodes, d.stream)) return rc;
     if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
@@ -162,9 +168,11 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     std::vector<float> lut(p.gamma_lut, p.gamma_lut + 256);
     if (int rc = d.lut.upload(lut, d.stream)) return rc;
     rt::fill_scene_constants(sc, p, d.scene);
-    d.scene.scene.nodes = d.nodes.p;
+    d.scene.scene.nodes = d.nodes.p;  // null unless RT_EXT_QNODE=0: the device traverses the quantised copy
+    d.scene.scene.qnodes = d.qnodes.p;
     d.scene.scene.tris = d.tris.p;
     d.scene.light.nodes = d.lnodes.p;
+    d.scene.light.qnodes = nullptr;
     d.scene.light.tris = d.ltris.p;
     d.scene.attrs = d.attrs.p;
     d.scene.tangents = p.tangents.empty() ? nullptr : d.tangents.p;
@@ -367,7 +375,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        d.nodes.release(); d.lnodes.release(); d.tris.release(); d.ltris.release(); d.attrs.release();
+        d.qnodes.release(); d.nodes.release(); d.lnodes.release(); d.tris.release(); d.ltris.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }

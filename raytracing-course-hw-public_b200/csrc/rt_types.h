@@ -7,6 +7,11 @@
 //   DNode  64 B  one per INNER node of the reference tree: both children's boxes + child links.
 //                The reference tests both child boxes at the parent (bvh.h:205-212), so one
 //                64 B fetch replaces two 40 B node fetches.
+//   QNode  32 B  the same inner node with both child boxes quantised to 8 bits per plane on a per-node
+//                power-of-two grid (conservative: the decoded box always contains the exact one), so
+//                that one node visit is ONE 32-byte sector / one 256-bit load.  k_extend is bound by
+//                the L1 data pipe, which moves one sector per cycle for divergent addresses, so bytes
+//                per node visit are what the traversal rate is made of ("k_extend").
 //   DTri   64 B  triangle in BVH order: a, (b-a), (c-a) + scene.objects id + end-of-leaf flag, padded to
 //                64 B so that it is two 256-bit loads (LDG.E.256 on sm_100a) inside one 128 B line.
 //   DAttr  64 B  per-vertex normals + uv + material id, BVH order (read once per shade).
@@ -30,6 +35,19 @@ struct alignas(64) DNode {
     float rminz, rmaxx, rmaxy, rmaxz;
     int32_t left, right;  // links
     int32_t pad0, pad1;
+};
+
+// Grid: plane(axis, q) = org[axis] + q * cell[axis], q in [0, 255].
+//   org[axis]  = the float whose bits are the whole word org[axis] (so the low byte, which holds the
+//                cell exponent, is part of the origin's mantissa; the packer rounds such that this
+//                value is <= the exact minimum); bit 8 is always 0.
+//   cell[axis] = 2^(e - 127), e = org[axis] & 0xFF (a float exponent field).
+//   q[0] bytes: l.minx l.miny l.minz l.maxx   q[1]: l.maxy l.maxz r.minx r.miny   q[2]: r.minz r.maxx r.maxy r.maxz
+//   (the plane order of DNode).
+struct alignas(32) QNode {
+    uint32_t org[3];
+    uint32_t q[3];
+    int32_t left, right;  // links
 };
 
 struct alignas(64) DTri {
@@ -76,7 +94,8 @@ struct alignas(16) DLight {  // light triangle extras, light-BVH order
 };
 
 struct DBvh {
-    const DNode *nodes;
+    const DNode *nodes;    // full-precision nodes (light BVH traversal, host checks); may be null on the device
+    const QNode *qnodes;   // quantised nodes (k_extend); null for the light BVH
     const DTri *tris;
     int32_t root;  // link; RT_LINK_NONE when empty
     uint32_t n_tris;

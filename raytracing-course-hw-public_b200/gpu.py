@@ -8,7 +8,8 @@ import numpy as np
 from . import _abi
 from ._abi import (RT_FLAG_ACCUMULATE, RT_MODE_BEAUTY, RT_MODE_PRIMARY_IDS, rt_render_params, rt_scene_desc, rt_stats)
 
-LIB_PATH = os.path.join(_abi.PKG_DIR, "librt_gpu.so")
+# RT_GPU_LIB selects another build of the same C ABI (kernel A/B experiments, tools/build_variants.sh)
+LIB_PATH = os.environ.get("RT_GPU_LIB") or os.path.join(_abi.PKG_DIR, "librt_gpu.so")
 
 # every symbol include/rt_gpu.h declares
 SYMBOLS = ["rt_gpu_create", "rt_gpu_destroy", "rt_gpu_upload_scene", "rt_gpu_render", "rt_gpu_readback",

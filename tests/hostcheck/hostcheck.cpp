@@ -22,6 +22,8 @@ int build(const rt_scene_desc *sc, HostScene &hs) {
     if (int rc = pack_scene(*sc, hs.p)) return rc;
     fill_scene_constants(*sc, hs.p, hs.d);
     hs.d.scene.nodes = hs.p.scene.nodes.data();
+    hs.d.scene.qnodes = hs.p.scene.qnodes.data();
+    hs.d.light.qnodes = hs.p.light.qnodes.data();
     hs.d.scene.tris = hs.p.scene.tris.data();
     hs.d.light.nodes = hs.p.light.nodes.data();
     hs.d.light.tris = hs.p.light.tris.data();
@@ -61,6 +63,66 @@ int hc_primary_ids(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids
             const Hit hit = closest_hit(hs.d.scene, cam.pos, dir, hs.d.eps);
             ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
         }
+    return 0;
+}
+
+// Same through the quantised nodes in the kernel's arithmetic (closest_hit_q == what k_extend does per ray).
+int hc_primary_ids_q(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    const Camera cam = make_camera(hs.d, w, h);
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
+            const Hit hit = closest_hit_q(hs.d.scene, cam.pos, dir, hs.d.eps);
+            ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
+        }
+    return 0;
+}
+
+// Quantised-node invariants over the whole scene BVH.  out[0] = nodes, out[1] = planes whose decoded position
+// (exact arithmetic: org + q * cell) is on the wrong side of the exact plane (must be 0), out[2] = planes with
+// less than 1/128 cell of slack (must be 0: the packer keeps 1/64), out[3..4] = summed surface area of the exact
+// / decoded child boxes (how much looser the quantised tree is).
+int hc_qnode_check(const rt_scene_desc *sc, double *out) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    const PackedBvh &b = hs.p.scene;
+    if (b.qnodes.size() != b.nodes.size()) return -100;
+    double bad = 0, tight = 0, area_exact = 0, area_q = 0;
+    for (size_t i = 0; i < b.nodes.size(); ++i) {
+        const DNode &n = b.nodes[i];
+        const QNode &q = b.qnodes[i];
+        if (q.left != n.left || q.right != n.right) return -101;
+        const float exact[12] = {n.lminx, n.lminy, n.lminz, n.lmaxx, n.lmaxy, n.lmaxz,
+                                 n.rminx, n.rminy, n.rminz, n.rmaxx, n.rmaxy, n.rmaxz};
+        double dec[12];
+        for (int k = 0; k < 12; ++k) {
+            const int axis = k % 3;
+            const bool is_max = (k / 3) & 1;
+            const uint32_t word = q.org[axis];
+            if (word & 0x100u) return -102;
+            const double org = (double)u2f(word), cell = ldexp(1.0, (int)(word & 255u) - 127);
+            const uint32_t byte = (q.q[k / 4] >> (8 * (k % 4))) & 255u;
+            dec[k] = org + byte * cell;
+            const double slack = is_max ? dec[k] - (double)exact[k] : (double)exact[k] - dec[k];
+            if (slack < 0) ++bad;
+            else if (slack < cell / 128) ++tight;
+        }
+        for (int c = 0; c < 2; ++c) {
+            const float *e = exact + 6 * c;
+            const double *d = dec + 6 * c;
+            const double ex = e[3] - e[0], ey = e[4] - e[1], ez = e[5] - e[2];
+            const double dx = d[3] - d[0], dy = d[4] - d[1], dz = d[5] - d[2];
+            area_exact += 2 * (ex * ey + ey * ez + ez * ex);
+            area_q += 2 * (dx * dy + dy * dz + dz * dx);
+        }
+    }
+    out[0] = (double)b.nodes.size();
+    out[1] = bad;
+    out[2] = tight;
+    out[3] = area_exact;
+    out[4] = area_q;
     return 0;
 }
 

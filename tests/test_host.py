@@ -142,6 +142,45 @@ def test_repacked_traversal_gives_reference_ids(name, hc, manifest, golden_scene
     assert (ids == ref).mean() >= 0.999
 
 
+@pytest.mark.parametrize("name", SMALL)
+def test_quantised_node_traversal_gives_reference_ids(name, hc, manifest, golden_scene):
+    """k_extend's per-ray arithmetic (32-byte quantised nodes, fused o/d slab test) finds the reference's hits."""
+    m = manifest["scenes"][name]
+    w, h = m["width"], m["height"]
+    d = golden_scene(name).desc()
+    ids = np.zeros((h, w), np.int32)
+    assert hc.hc_primary_ids_q(C.byref(d), w, h, ids.ctypes.data_as(C.c_void_p)) == 0
+    ref = golden_array(f"{name}_ids.i32", np.int32, (h, w))
+    assert (ids == ref).mean() >= 0.999
+
+
+def _qnode_check(hc, scene):
+    d = scene.desc()
+    out = (C.c_double * 5)()
+    assert hc.hc_qnode_check(C.byref(d), out) == 0
+    return list(out)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_quantised_nodes_are_conservative(name, hc, golden_scene):
+    n, bad, tight, area_exact, area_q = _qnode_check(hc, golden_scene(name))
+    assert n > 0 and bad == 0 and tight == 0
+    assert area_q >= area_exact
+
+
+def test_quantised_nodes_are_conservative_on_the_260k_scene(hc, big_scene):
+    n, bad, tight, area_exact, area_q = _qnode_check(hc, big_scene)
+    assert n > 70000 and bad == 0 and tight == 0
+    # 8 bits per plane on a per-node grid: the decoded boxes are only a few percent larger
+    assert 1.0 <= area_q / area_exact < 1.10
+    ids_q = np.zeros((96, 96), np.int32)
+    ids = np.zeros((96, 96), np.int32)
+    d = big_scene.desc()
+    assert hc.hc_primary_ids_q(C.byref(d), 96, 96, ids_q.ctypes.data_as(C.c_void_p)) == 0
+    assert hc.hc_primary_ids(C.byref(d), 96, 96, ids.ctypes.data_as(C.c_void_p)) == 0
+    assert (ids_q == ids).mean() >= 0.999
+
+
 def test_device_philox_matches_known_answers(hc):
     out = (C.c_uint32 * 4)()
     hc.hc_philox((C.c_uint32 * 4)(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344),
