@@ -40,6 +40,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to
+# stdout), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a
+# private duplicate of the original stdout.
+_RESULT_FD = None
+
+
+def _capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def scene_path(name):
     """Deterministic synthetic scene, generated on first use (one private copy per rank: no write races)."""
     import gen_gltf
@@ -174,7 +197,7 @@ def run_reference_arm(args, rank):
            "cpu_baseline": {**vals[-1], "value": v},
            "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def config_dict(n_gpus, extra=None):
@@ -320,7 +343,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                "kernel_ms_profiled_step": kernel_ms, "reference_work_per_ray": counts,
                "host_s": {"load_and_bvh_build": t_load, "first_upload": t_upload},
                "vs_baseline_note": "0.355 Msamples/s = README.md:4 (Sponza 1000x1000x1000spp in ~47 min, unknown CPU)"}
-        print(json.dumps(out), flush=True)
+        emit(out)
     barrier()
     rt.close()
     if world > 1:
@@ -339,6 +362,7 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP_PER_GPU, help="samples per pixel per GPU")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
+    _capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
