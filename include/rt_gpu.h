@@ -116,7 +116,7 @@ typedef struct rt_scene_desc {
     uint32_t ray_depth;       /* Scene::ray_depth = DEFAULT_RAY_DEPTH = 8 */
     uint32_t n_materials;
     uint32_t n_textures;
-    uint32_t _pad0;
+    uint32_t flags;           /* RT_SCENE_* bits; 0 = defaults */
     uint64_t texel_bytes;
     /* per-triangle arrays in scene.objects order (Object, geometry.h:639-659) */
     const float *tri_pos;          /* n_tris*9: a,b,c            */
@@ -130,6 +130,12 @@ typedef struct rt_scene_desc {
     rt_bvh_desc scene_bvh;         /* over all triangles (raytracer.h:441-443) */
     rt_bvh_desc light_bvh;         /* over emission != 0 (raytracer.h:444-447) */
 } rt_scene_desc;
+
+/* rt_scene_desc.flags */
+#define RT_SCENE_KEEP_HOST_BVH 1u /* traverse scene_bvh exactly as passed; default: the library rebuilds the
+                                     scene BVH over the same triangles with its own SAH builder (closest hits do
+                                     not depend on the tree; the reference's builder minimises a mis-stated
+                                     surface area, src/geometry.h:419-421, and costs ~25 % more work per ray) */
 
 typedef enum rt_render_mode {
     RT_MODE_BEAUTY = 0,      /* jittered Monte-Carlo estimate (render_pixel, raytracer.h:618) */

@@ -64,7 +64,7 @@ class rt_scene_desc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("n_tris", C.c_uint32), ("camera", rt_camera), ("bg_color", C.c_float * 3),
         ("eps", C.c_float), ("min_roughness", C.c_float), ("vndf_factor", C.c_float), ("ray_depth", C.c_uint32),
-        ("n_materials", C.c_uint32), ("n_textures", C.c_uint32), ("_pad0", C.c_uint32), ("texel_bytes", C.c_uint64),
+        ("n_materials", C.c_uint32), ("n_textures", C.c_uint32), ("flags", C.c_uint32), ("texel_bytes", C.c_uint64),
         ("tri_pos", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_uv", C.c_void_p), ("tri_tangents", C.c_void_p),
         ("tri_material", C.c_void_p), ("materials", C.c_void_p), ("textures", C.c_void_p), ("texels", C.c_void_p),
         ("scene_bvh", rt_bvh_desc), ("light_bvh", rt_bvh_desc),

@@ -12,6 +12,7 @@
 
 #include "rt_gpu.h"
 #include "rt_types.h"
+#include "sah_build.h"
 
 namespace rt {
 
@@ -208,11 +209,19 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     return detail::quantize_nodes(out.nodes, out.qnodes);
 }
 
-inline int pack_scene(const rt_scene_desc &sc, PackedScene &out) {
-    if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene)) return rc;
+// `rebuild_scene_bvh`: build the scene BVH with the library's SAH builder (sah_build.h) over the triangles of
+// sc.scene_bvh instead of adopting the host's tree; the light BVH is always adopted as passed.
+inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false) {
+    if (rebuild_scene_bvh && sc.scene_bvh.n_objects > 0 && sc.scene_bvh.root != RT_NO_CHILD) {
+        BuiltBvh built;
+        build_sah_bvh(sc.tri_pos, sc.scene_bvh.objects, sc.scene_bvh.n_objects, built);
+        if (int rc = pack_bvh(sc, built.desc(), out.scene)) return rc;
+    } else if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene)) {
+        return rc;
+    }
     if (int rc = pack_bvh(sc, sc.light_bvh, out.light)) return rc;
 
-    const uint32_t n = sc.scene_bvh.n_objects;
+    const uint32_t n = static_cast<uint32_t>(out.scene.order.size());  // device triangle order = packed BVH order
     out.attrs.resize(n);
     bool any_tangent = false;
     if (sc.tri_tangents)
@@ -223,7 +232,7 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out) {
     out.tangents.clear();
     if (any_tangent) out.tangents.resize(n);
     for (uint32_t k = 0; k < n; ++k) {
-        const uint32_t id = sc.scene_bvh.objects[k];
+        const uint32_t id = out.scene.order[k];
         const float *nn = sc.tri_normals + static_cast<size_t>(id) * 9;
         const float *uv = sc.tri_uv + static_cast<size_t>(id) * 6;
         DAttr &a = out.attrs[k];

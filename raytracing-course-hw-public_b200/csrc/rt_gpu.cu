@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -418,7 +419,9 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
             return fail(RT_ERR_BAD_SCENE, "texture extent out of range");
     }
     rt::PackedScene packed;
-    if (int rc = rt::pack_scene(*scene, packed)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    const char *keep_env = std::getenv("RT_KEEP_HOST_BVH");  // A/B switch for measurements
+    const bool keep = (scene->flags & RT_SCENE_KEEP_HOST_BVH) || (keep_env && std::atoi(keep_env) != 0);
+    if (int rc = rt::pack_scene(*scene, packed, !keep)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
     for (auto &d : ctx->devs)
         if (int rc = upload_to_device(*d, *scene, packed)) return rc;
     ctx->ray_depth = scene->ray_depth;

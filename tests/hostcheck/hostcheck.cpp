@@ -3,6 +3,7 @@
 // functions the CUDA kernels call (traversal, hit shading data, samplers, pdfs, BRDF, Philox lanes)
 // with the oracle without a GPU.  It is NOT a render path of the product: librt_gpu.so does not
 // contain or call any of this, and nothing outside tests/ builds or loads it.
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -18,8 +19,10 @@ struct HostScene {
     DScene d;
 };
 
+bool g_rebuild = false;  // hc_set_rebuild: pack with the library's SAH builder instead of the host's tree
+
 int build(const rt_scene_desc *sc, HostScene &hs) {
-    if (int rc = pack_scene(*sc, hs.p)) return rc;
+    if (int rc = pack_scene(*sc, hs.p, g_rebuild)) return rc;
     fill_scene_constants(*sc, hs.p, hs.d);
     hs.d.scene.nodes = hs.p.scene.nodes.data();
     hs.d.scene.qnodes = hs.p.scene.qnodes.data();
@@ -52,6 +55,62 @@ Camera make_camera(const DScene &d, uint32_t w, uint32_t h) {
 }  // namespace
 
 extern "C" {
+
+void hc_set_rebuild(int on) { g_rebuild = on != 0; }
+
+// Build statistics of the library's SAH builder: out[0] = seconds, out[1] = inner nodes, out[2] = leaves,
+// out[3] = max leaf size, out[4] = max depth, out[5] = 1 when every triangle id appears exactly once.
+int hc_sah_stats(const rt_scene_desc *sc, double *out) {
+    BuiltBvh b;
+    const auto t0 = std::chrono::steady_clock::now();
+    build_sah_bvh(sc->tri_pos, sc->scene_bvh.objects, sc->scene_bvh.n_objects, b);
+    out[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    double inner = 0, leaves = 0, max_leaf = 0;
+    std::vector<int> depth(b.nodes.size(), -1);
+    std::vector<uint32_t> todo;
+    int max_depth = 0;
+    std::vector<uint8_t> seen(sc->n_tris, 0);
+    bool once = true;
+    if (b.root != RT_NO_CHILD && !b.objects.empty()) {
+        todo.push_back(b.root);
+        depth[b.root] = 0;
+    }
+    while (!todo.empty()) {
+        const uint32_t i = todo.back();
+        todo.pop_back();
+        const rt_bvh_node &nd = b.nodes[i];
+        max_depth = std::max(max_depth, depth[i]);
+        if (nd.left_child == RT_NO_CHILD && nd.right_child == RT_NO_CHILD) {
+            ++leaves;
+            max_leaf = std::max(max_leaf, (double)(nd.obj_end - nd.obj_begin));
+            for (uint32_t k = nd.obj_begin; k < nd.obj_end; ++k) {
+                const uint32_t id = b.objects[k];
+                if (id >= sc->n_tris || seen[id]) once = false;
+                else seen[id] = 1;
+                // the leaf box must contain the triangle
+                for (int v = 0; v < 3; ++v)
+                    for (int a = 0; a < 3; ++a) {
+                        const float x = sc->tri_pos[(size_t)id * 9 + v * 3 + a];
+                        if (x < nd.bmin[a] || x > nd.bmax[a]) once = false;
+                    }
+            }
+        } else {
+            ++inner;
+            for (uint32_t c : {nd.left_child, nd.right_child}) {
+                if (c == RT_NO_CHILD || c >= b.nodes.size()) return -1;
+                const rt_bvh_node &ch = b.nodes[c];
+                for (int a = 0; a < 3; ++a)
+                    if (ch.bmin[a] < nd.bmin[a] || ch.bmax[a] > nd.bmax[a]) once = false;  // child box inside parent box
+                depth[c] = depth[i] + 1;
+                todo.push_back(c);
+            }
+        }
+    }
+    for (uint32_t k = 0; k < sc->scene_bvh.n_objects; ++k)
+        if (!seen[sc->scene_bvh.objects[k]]) once = false;
+    out[1] = inner; out[2] = leaves; out[3] = max_leaf; out[4] = max_depth; out[5] = once ? 1.0 : 0.0;
+    return 0;
+}
 
 int hc_primary_ids(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids) {
     HostScene hs;

@@ -181,6 +181,48 @@ def test_quantised_nodes_are_conservative_on_the_260k_scene(hc, big_scene):
     assert (ids_q == ids).mean() >= 0.999
 
 
+# ---- the library's own SAH builder (csrc/sah_build.h) ------------------------------------------------------
+@pytest.mark.parametrize("name", SMALL)
+def test_sah_rebuilt_tree_gives_reference_ids(name, hc, manifest, golden_scene):
+    """Closest hits do not depend on the tree: traversal of the library-built BVH (both node formats) finds the
+    reference's primary ids."""
+    m = manifest["scenes"][name]
+    w, h = m["width"], m["height"]
+    d = golden_scene(name).desc()
+    ref = golden_array(f"{name}_ids.i32", np.int32, (h, w))
+    hc.hc_set_rebuild(1)
+    try:
+        for fn in (hc.hc_primary_ids, hc.hc_primary_ids_q):
+            ids = np.zeros((h, w), np.int32)
+            assert fn(C.byref(d), w, h, ids.ctypes.data_as(C.c_void_p)) == 0
+            assert (ids == ref).mean() >= 0.999
+        out = (C.c_double * 5)()
+        assert hc.hc_qnode_check(C.byref(d), out) == 0 and out[1] == 0 and out[2] == 0
+    finally:
+        hc.hc_set_rebuild(0)
+
+
+def test_sah_builder_invariants_on_the_260k_scene(hc, big_scene):
+    d = big_scene.desc()
+    out = (C.c_double * 6)()
+    assert hc.hc_sah_stats(C.byref(d), out) == 0
+    secs, inner, leaves, max_leaf, max_depth, ok = list(out)
+    print(f"sah build: {secs * 1e3:.0f} ms, {inner:.0f} inner, {leaves:.0f} leaves, max leaf {max_leaf:.0f}, depth {max_depth:.0f}")
+    assert ok == 1.0  # every triangle exactly once, boxes nested
+    assert inner == leaves - 1 and max_leaf <= 8 and max_depth < 62
+    hc.hc_set_rebuild(1)
+    try:
+        ids = np.zeros((96, 96), np.int32)
+        ids_q = np.zeros((96, 96), np.int32)
+        assert hc.hc_primary_ids(C.byref(d), 96, 96, ids.ctypes.data_as(C.c_void_p)) == 0
+        assert hc.hc_primary_ids_q(C.byref(d), 96, 96, ids_q.ctypes.data_as(C.c_void_p)) == 0
+    finally:
+        hc.hc_set_rebuild(0)
+    host_tree = np.zeros((96, 96), np.int32)
+    assert hc.hc_primary_ids(C.byref(d), 96, 96, host_tree.ctypes.data_as(C.c_void_p)) == 0
+    assert (ids == host_tree).mean() >= 0.999 and (ids_q == host_tree).mean() >= 0.999
+
+
 def test_device_philox_matches_known_answers(hc):
     out = (C.c_uint32 * 4)()
     hc.hc_philox((C.c_uint32 * 4)(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344),
@@ -205,10 +247,20 @@ def test_device_hit_data_matches_reference(name, hc, manifest, golden_scene):
     assert diff.max() < 5e-3
 
 
+@pytest.mark.parametrize("rebuild", [0, 1])
 @pytest.mark.parametrize("name,tol_frac", [("tiny", 0.01), ("small_lights", 0.02)])
-def test_device_math_follows_oracle_paths(name, tol_frac, hc, manifest, golden_scene):
+def test_device_math_follows_oracle_paths(name, tol_frac, rebuild, hc, manifest, golden_scene):
     """Same Philox keys -> same paths: per-pixel means agree to float noise for all but the few pixels where a
-    rounding difference flipped a discrete decision."""
+    rounding difference flipped a discrete decision.  `rebuild`: with the library's own SAH tree instead of the
+    host's (triangle attributes follow the packed order)."""
+    hc.hc_set_rebuild(rebuild)
+    try:
+        _follow_oracle_paths(name, tol_frac, hc, manifest, golden_scene)
+    finally:
+        hc.hc_set_rebuild(0)
+
+
+def _follow_oracle_paths(name, tol_frac, hc, manifest, golden_scene):
     m = manifest["scenes"][name]
     w, h = m["width"] // 2, m["height"] // 2
     sc = golden_scene(name)
