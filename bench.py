@@ -318,8 +318,16 @@ def run_gpu_arm(args, rank, world, local_rank):
         flop_per_ray = FLOP_BOX * counts["box_tests_per_ray"] + FLOP_TRI * counts["tri_tests_per_ray"]
         n_ext_launches = max(1, (pst["kernel_launches"] // (2 + 2 * scene.ray_depth)) * scene.ray_depth)
         achieved = flop_per_ray * pst["extension_rays"] / (pst["kernel_ms"][1] * 1e-3) / 1e12
+        traffic = traffic_note = None
+        try:  # DRAM bytes per extension ray of k_extend from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", "k_extend_dram.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_ray"] * pst["extension_rays"] / n_ext_launches
+            traffic_note = tj["note"]
+        except (OSError, KeyError, ValueError):
+            pass
         roof = {"bound": "fp32", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "measured on this GPU by rt_gpu_fp32_peak (FFMA loop); MEASURED_PEAKS.json has no FP32 "
                                "entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "algorithmic_flop_per_ray": flop_per_ray, "rays_per_launch": pst["extension_rays"] / n_ext_launches,

@@ -168,6 +168,55 @@ typedef struct rt_stats {
     uint64_t kernel_launches;  /* kernels launched by the last rt_gpu_render */
 } rt_stats;
 
+/* ---- course text scenes (sample_data/scene-*.txt, homebrew_primitives/*.txt) -------------------------
+ * PARITY UNPINNED: the reference at HEAD cannot load or render these (no parser, triangle-only geometry,
+ * no delta lights, no refraction).  The structures follow the file grammar; the
+ * semantics are documented in csrc/text_core.cuh.  Scenes are tiny (<= RT_TEXT_MAX_PRIMS primitives), so
+ * the device intersects every primitive per ray (planes are unbounded: no BVH). */
+#define RT_TEXT_MAX_PRIMS 256
+#define RT_TEXT_MAX_LIGHTS 64
+#define RT_TEXT_MAX_DEPTH 16
+
+enum { RT_PRIM_PLANE = 0, RT_PRIM_ELLIPSOID = 1, RT_PRIM_BOX = 2, RT_PRIM_TRIANGLE = 3 };
+enum { RT_MAT_DIFFUSE = 0, RT_MAT_METALLIC = 1, RT_MAT_DIELECTRIC = 2 };
+enum { RT_LIGHT_DIRECTIONAL = 0, RT_LIGHT_POINT = 1 };
+enum { RT_SHADE_FLAT = 0,     /* colour of the nearest primitive (scene-000.txt) */
+       RT_SHADE_WHITTED = 1,  /* ambient + delta lights + mirror + Fresnel refraction, RAY_DEPTH (scene-001..004) */
+       RT_SHADE_PATH = 2 };   /* Monte-Carlo path tracing, SAMPLES, EMISSION (practice3_*, practice5_*) */
+
+typedef struct rt_text_prim {
+    uint32_t kind;      /* RT_PRIM_* */
+    uint32_t material;  /* RT_MAT_* */
+    float param[9];     /* PLANE: normal; ELLIPSOID: semi-axes; BOX: half extents; TRIANGLE: three vertices */
+    float position[3];  /* POSITION (default 0) */
+    float rotation[4];  /* ROTATION x y z w (default 0 0 0 1), src/geometry.h:154-156 */
+    float color[3];     /* COLOR */
+    float emission[3];  /* EMISSION */
+    float ior;          /* IOR */
+} rt_text_prim;
+
+typedef struct rt_text_light {
+    uint32_t kind;         /* RT_LIGHT_* */
+    float intensity[3];    /* LIGHT_INTENSITY */
+    float vec[3];          /* LIGHT_DIRECTION (towards the light) or LIGHT_POSITION */
+    float attenuation[3];  /* LIGHT_ATTENUATION c0 c1 c2: I / (c0 + c1 r + c2 r^2) */
+} rt_text_light;
+
+typedef struct rt_text_scene {
+    uint32_t abi_version;  /* RT_GPU_ABI_VERSION */
+    uint32_t width, height;     /* DIMENSIONS (informative; rt_render_params decides) */
+    uint32_t ray_depth;         /* RAY_DEPTH, default 1 (Scene::ray_depth, src/scene.h:76) */
+    uint32_t samples;           /* SAMPLES, default 1 (Scene::samples, src/scene.h:77) */
+    uint32_t shading;           /* RT_SHADE_* */
+    uint32_t n_prims, n_lights;
+    float bg_color[3];          /* BG_COLOR */
+    float ambient[3];           /* AMBIENT_LIGHT */
+    rt_camera camera;
+    float eps;                  /* 1e-4, src/config.h:15 */
+    const rt_text_prim *prims;
+    const rt_text_light *lights;
+} rt_text_scene;
+
 typedef struct rt_gpu_ctx rt_gpu_ctx;
 
 /* n_gpus devices starting at first_device (single-process multi-device: one
@@ -177,6 +226,10 @@ int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device);
 void rt_gpu_destroy(rt_gpu_ctx *ctx);
 
 int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene);
+
+/* Upload a course text scene instead of a triangle scene; rt_gpu_render / rt_gpu_readback then work on it
+ * (RT_MODE_PRIMARY_IDS gives the primitive index per pixel).  Parity unpinned, see above. */
+int rt_gpu_upload_text_scene(rt_gpu_ctx *ctx, const rt_text_scene *scene);
 
 /* Asynchronous with respect to the host only inside the call: returns after
  * the device work (and, for n_gpus > 1, the reduce to device 0) completed. */

@@ -45,6 +45,16 @@ int rt_host_build_bvh(const float *tri_pos, uint32_t n_tris, const uint8_t *sele
                       uint32_t min_node_size, uint32_t max_depth, rt_bvh_build *out);
 void rt_host_free_bvh(rt_bvh_build *bvh);
 
+/* ---- course text scenes (sample_data/scene-*.txt; PARITY UNPINNED, see rt_gpu.h) ---------------------------
+ * Grammar (one command per line): DIMENSIONS, RAY_DEPTH, SAMPLES, BG_COLOR, AMBIENT_LIGHT,
+ * CAMERA_POSITION/RIGHT/UP/FORWARD, CAMERA_FOV_X, NEW_PRIMITIVE {PLANE|ELLIPSOID|BOX|TRIANGLE, POSITION, ROTATION,
+ * COLOR, METALLIC, DIELECTRIC, IOR, EMISSION}, NEW_LIGHT {LIGHT_INTENSITY, LIGHT_DIRECTION | LIGHT_POSITION,
+ * LIGHT_ATTENUATION}.  Shading: SAMPLES present -> RT_SHADE_PATH; else any of NEW_LIGHT / RAY_DEPTH /
+ * AMBIENT_LIGHT -> RT_SHADE_WHITTED; else RT_SHADE_FLAT.  Unknown commands are an error (RT_ERR_BAD_SCENE).
+ * One malloc block; free with rt_text_scene_free. */
+int rt_text_scene_parse(const char *path, rt_text_scene **out);
+void rt_text_scene_free(rt_text_scene *scene);
+
 /* ---- image (src/image.h:34-82) ------------------------------------------------------------ */
 void rt_host_tonemap_rgb8(const float *rgb_mean, size_t n_pixels, uint8_t *rgb8);
 int rt_host_write_ppm(const char *path, const uint8_t *rgb8, uint32_t width, uint32_t height);

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "text_kernels.cuh"
 #include "repack.h"
 #include "rt_gpu.h"
 
@@ -115,6 +116,12 @@ struct DeviceState {
     DevBuf<uint32_t> texels;
     DevBuf<float> lut;
     DScene scene;
+    // course text scene (rt_gpu_upload_text_scene)
+    DevBuf<rt_text_prim> tprims;
+    DevBuf<rt_text_light> tlights;
+    DevBuf<uint32_t> temit;
+    rtt::TextScene tscene;
+    rt_camera tcamera;
     // render state
     DevBuf<float4> qo[2], qd[2], qthr[2], hit, rad, accum;
     DevBuf<uint32_t> counters;
@@ -143,6 +150,7 @@ struct rt_gpu_ctx {
     std::vector<std::unique_ptr<DeviceState>> devs;
     std::vector<ncclComm_t> comms;
     bool have_scene = false, have_render = false, profiling = false;
+    bool text_scene = false;  // the uploaded scene is a course text scene
     rt_render_params last{};
     rt_stats stats{};
     uint32_t ray_depth = 0;
@@ -205,6 +213,55 @@ void mark(rt_gpu_ctx *ctx, DeviceState &d, int kind) {
     cudaEvent_t e = d.next_event();
     cudaEventRecord(e, d.stream);
     d.marks.emplace_back(e, kind);
+}
+
+// Course text scene: one launch, one thread per pixel (text_kernels.cuh).
+int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, uint32_t s_begin, uint32_t s_end,
+                        uint64_t &launches) {
+    CU_CHECK(cudaSetDevice(d.device));
+    const uint32_t W = rp.width, H = rp.height;
+    const size_t n_pix = static_cast<size_t>(W) * H;
+    if (int rc = d.accum.alloc(n_pix)) return rc;
+    if (int rc = d.stats.alloc(4)) return rc;
+    const bool ids_mode = rp.mode == RT_MODE_PRIMARY_IDS;
+    if (ids_mode) {
+        if (int rc = d.prim_ids.alloc(n_pix)) return rc;
+    } else if (!(rp.flags & RT_FLAG_ACCUMULATE)) {
+        CU_CHECK(cudaMemsetAsync(d.accum.p, 0, n_pix * sizeof(float4), d.stream));
+    }
+    d.marks.clear();
+    d.events_used = 0;
+    CU_CHECK(cudaEventRecord(d.ev_begin, d.stream));
+    mark(ctx, d, -1);
+    const unsigned long long hs[4] = {0, 0, 0, ids_mode ? 0ull : static_cast<unsigned long long>(n_pix) * (s_end - s_begin)};
+    CU_CHECK(cudaMemcpyAsync(d.stats.p, hs, sizeof hs, cudaMemcpyHostToDevice, d.stream));
+    if (ids_mode || (s_end > s_begin && d.tscene.ray_depth > 0)) {
+        rt::Camera cam;
+        DScene tmp;
+        std::memset(&tmp, 0, sizeof tmp);
+        for (int k = 0; k < 3; ++k) {
+            tmp.cam_pos[k] = d.tcamera.position[k];
+            tmp.cam_right[k] = d.tcamera.right[k];
+            tmp.cam_up[k] = d.tcamera.up[k];
+            tmp.cam_fwd[k] = d.tcamera.forward[k];
+        }
+        tmp.fov_x = d.tcamera.fov_x;
+        cam = make_camera(tmp, W, H);
+        rtt::TextParams tp;
+        tp.width = W;
+        tp.height = H;
+        tp.s0 = s_begin;
+        tp.s1 = s_end;
+        tp.k0 = static_cast<uint32_t>(rp.seed);
+        tp.k1 = static_cast<uint32_t>(rp.seed >> 32);
+        tp.ids = ids_mode ? 1u : 0u;
+        rtt::k_text_render<<<static_cast<unsigned>((n_pix + 127) / 128), 128, 0, d.stream>>>(d.tscene, cam, tp, d.accum.p, d.prim_ids.p);
+        mark(ctx, d, K_SHADE);
+        launches += 1;
+    }
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
+    return RT_OK;
 }
 
 // Enqueue the whole render of samples [s_begin, s_end) on device d (asynchronous).
@@ -376,7 +433,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        d.qnodes.release(); d.nodes.release(); d.lnodes.release(); d.tris.release(); d.ltris.release(); d.attrs.release();
+        d.qnodes.release(); d.nodes.release(); d.lnodes.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }
@@ -427,6 +484,52 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     ctx->ray_depth = scene->ray_depth;
     ctx->have_scene = true;
     ctx->have_render = false;
+    ctx->text_scene = false;
+    return RT_OK;
+}
+
+int rt_gpu_upload_text_scene(rt_gpu_ctx *ctx, const rt_text_scene *scene) {
+    if (!ctx || !scene) return fail(RT_ERR_INVALID_ARG, "rt_gpu_upload_text_scene: null argument");
+    if (scene->abi_version != RT_GPU_ABI_VERSION) return fail(RT_ERR_INVALID_ARG, "rt_gpu_upload_text_scene: ABI version mismatch");
+    if (scene->n_prims > RT_TEXT_MAX_PRIMS || scene->n_lights > RT_TEXT_MAX_LIGHTS || scene->ray_depth > RT_TEXT_MAX_DEPTH ||
+        scene->shading > RT_SHADE_PATH || (scene->n_prims && !scene->prims) || (scene->n_lights && !scene->lights))
+        return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_text_scene: too many primitives / lights, depth > 16 or unknown shading");
+    std::vector<rt_text_prim> prims(scene->prims, scene->prims + scene->n_prims);
+    std::vector<rt_text_light> lights(scene->lights, scene->lights + scene->n_lights);
+    std::vector<uint32_t> emitters;
+    for (uint32_t i = 0; i < scene->n_prims; ++i) {
+        const rt_text_prim &p = prims[i];
+        if (p.kind > RT_PRIM_TRIANGLE || p.material > RT_MAT_DIELECTRIC) return fail(RT_ERR_BAD_SCENE, "unknown primitive kind / material");
+        const bool emits = p.emission[0] != 0.0f || p.emission[1] != 0.0f || p.emission[2] != 0.0f;
+        if (emits && p.kind != RT_PRIM_PLANE) emitters.push_back(i);  // an unbounded plane cannot be area-sampled
+    }
+    for (auto &dp : ctx->devs) {
+        DeviceState &d = *dp;
+        CU_CHECK(cudaSetDevice(d.device));
+        if (int rc = d.tprims.upload(prims, d.stream)) return rc;
+        if (int rc = d.tlights.upload(lights, d.stream)) return rc;
+        if (int rc = d.temit.upload(emitters, d.stream)) return rc;
+        rtt::TextScene &t = d.tscene;
+        t.prims = d.tprims.p;
+        t.lights = d.tlights.p;
+        t.emitters = d.temit.p;
+        t.n_prims = scene->n_prims;
+        t.n_lights = scene->n_lights;
+        t.n_emitters = static_cast<uint32_t>(emitters.size());
+        t.ray_depth = scene->ray_depth;
+        t.shading = scene->shading;
+        for (int k = 0; k < 3; ++k) {
+            t.bg[k] = scene->bg_color[k];
+            t.ambient[k] = scene->ambient[k];
+        }
+        t.eps = scene->eps;
+        d.tcamera = scene->camera;
+        CU_CHECK(cudaStreamSynchronize(d.stream));
+    }
+    ctx->ray_depth = scene->ray_depth;
+    ctx->have_scene = true;
+    ctx->have_render = false;
+    ctx->text_scene = true;
     return RT_OK;
 }
 
@@ -448,7 +551,11 @@ int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params) {
         const uint32_t se = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * (g + 1) / n);
         rt_render_params local = rp;
         if (rp.mode == RT_MODE_PRIMARY_IDS && g > 0) continue;  // ids: device 0 only
-        if (int rc = enqueue_render(ctx, *ctx->devs[g], local, sb, se, launches)) return rc;
+        if (ctx->text_scene) {
+            if (int rc = enqueue_text_render(ctx, *ctx->devs[g], local, sb, se, launches)) return rc;
+        } else if (int rc = enqueue_render(ctx, *ctx->devs[g], local, sb, se, launches)) {
+            return rc;
+        }
     }
     const size_t n_floats = static_cast<size_t>(rp.width) * rp.height * 4;
     if (n > 1 && rp.mode == RT_MODE_BEAUTY) {

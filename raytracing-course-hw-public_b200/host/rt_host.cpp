@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <string>
 #include <vector>
 
 namespace {
@@ -372,6 +373,110 @@ void rt_host_free_bvh(rt_bvh_build *bvh) {
     bvh->nodes = nullptr;
     bvh->objects = nullptr;
 }
+
+int rt_text_scene_parse(const char *path, rt_text_scene **out) {
+    if (!path || !out) return RT_ERR_INVALID_ARG;
+    *out = nullptr;
+    std::FILE *f = std::fopen(path, "r");
+    if (!f) return RT_ERR_INVALID_ARG;
+    rt_text_scene sc;
+    std::memset(&sc, 0, sizeof sc);
+    sc.abi_version = RT_GPU_ABI_VERSION;
+    sc.ray_depth = 1;  // Scene defaults, scene.h:76-77
+    sc.samples = 1;
+    sc.eps = 1e-4f;
+    sc.camera.right[0] = sc.camera.up[1] = 1.0f;
+    sc.camera.forward[2] = -1.0f;
+    sc.camera.fov_x = 1.5708f;
+    std::vector<rt_text_prim> prims;
+    std::vector<rt_text_light> lights;
+    bool has_samples = false, has_whitted = false;
+    int rc = RT_OK;
+    char line[1024];
+    enum { NONE, PRIM, LIGHT } cur = NONE;
+    auto floats = [](const char *s, float *dst, int n) {
+        for (int i = 0; i < n; ++i) {
+            char *end = nullptr;
+            dst[i] = std::strtof(s, &end);
+            if (end == s) return false;
+            s = end;
+        }
+        return true;
+    };
+    while (rc == RT_OK && std::fgets(line, sizeof line, f)) {
+        char cmd[64];
+        int used = 0;
+        if (std::sscanf(line, "%63s%n", cmd, &used) != 1) continue;  // blank line
+        const char *args = line + used;
+        const std::string c(cmd);
+        float v[9];
+        bool ok = true;
+        if (c == "DIMENSIONS") { ok = floats(args, v, 2); sc.width = (uint32_t)v[0]; sc.height = (uint32_t)v[1]; }
+        else if (c == "RAY_DEPTH") { ok = floats(args, v, 1); sc.ray_depth = (uint32_t)v[0]; has_whitted = true; }
+        else if (c == "SAMPLES") { ok = floats(args, v, 1); sc.samples = (uint32_t)v[0]; has_samples = true; }
+        else if (c == "BG_COLOR") ok = floats(args, sc.bg_color, 3);
+        else if (c == "AMBIENT_LIGHT") { ok = floats(args, sc.ambient, 3); has_whitted = true; }
+        else if (c == "CAMERA_POSITION") ok = floats(args, sc.camera.position, 3);
+        else if (c == "CAMERA_RIGHT") ok = floats(args, sc.camera.right, 3);
+        else if (c == "CAMERA_UP") ok = floats(args, sc.camera.up, 3);
+        else if (c == "CAMERA_FORWARD") ok = floats(args, sc.camera.forward, 3);
+        else if (c == "CAMERA_FOV_X") ok = floats(args, &sc.camera.fov_x, 1);
+        else if (c == "NEW_PRIMITIVE") {
+            rt_text_prim p;
+            std::memset(&p, 0, sizeof p);
+            p.kind = RT_PRIM_PLANE;
+            p.param[1] = 1.0f;
+            p.rotation[3] = 1.0f;
+            p.ior = 1.5f;  // material::ior default, geometry.h:609
+            prims.push_back(p);
+            cur = PRIM;
+        } else if (c == "NEW_LIGHT") {
+            rt_text_light l;
+            std::memset(&l, 0, sizeof l);
+            l.attenuation[0] = 1.0f;
+            lights.push_back(l);
+            cur = LIGHT;
+            has_whitted = true;
+        } else if (cur == PRIM && c == "PLANE") { prims.back().kind = RT_PRIM_PLANE; ok = floats(args, prims.back().param, 3); }
+        else if (cur == PRIM && c == "ELLIPSOID") { prims.back().kind = RT_PRIM_ELLIPSOID; ok = floats(args, prims.back().param, 3); }
+        else if (cur == PRIM && c == "BOX") { prims.back().kind = RT_PRIM_BOX; ok = floats(args, prims.back().param, 3); }
+        else if (cur == PRIM && c == "TRIANGLE") { prims.back().kind = RT_PRIM_TRIANGLE; ok = floats(args, prims.back().param, 9); }
+        else if (cur == PRIM && c == "POSITION") ok = floats(args, prims.back().position, 3);
+        else if (cur == PRIM && c == "ROTATION") ok = floats(args, prims.back().rotation, 4);
+        else if (cur == PRIM && c == "COLOR") ok = floats(args, prims.back().color, 3);
+        else if (cur == PRIM && c == "EMISSION") ok = floats(args, prims.back().emission, 3);
+        else if (cur == PRIM && c == "METALLIC") prims.back().material = RT_MAT_METALLIC;
+        else if (cur == PRIM && c == "DIELECTRIC") prims.back().material = RT_MAT_DIELECTRIC;
+        else if (cur == PRIM && c == "IOR") ok = floats(args, &prims.back().ior, 1);
+        else if (cur == LIGHT && c == "LIGHT_INTENSITY") ok = floats(args, lights.back().intensity, 3);
+        else if (cur == LIGHT && c == "LIGHT_DIRECTION") { lights.back().kind = RT_LIGHT_DIRECTIONAL; ok = floats(args, lights.back().vec, 3); }
+        else if (cur == LIGHT && c == "LIGHT_POSITION") { lights.back().kind = RT_LIGHT_POINT; ok = floats(args, lights.back().vec, 3); }
+        else if (cur == LIGHT && c == "LIGHT_ATTENUATION") ok = floats(args, lights.back().attenuation, 3);
+        else ok = false;
+        if (!ok) rc = RT_ERR_BAD_SCENE;
+    }
+    std::fclose(f);
+    if (rc != RT_OK) return rc;
+    if (prims.size() > RT_TEXT_MAX_PRIMS || lights.size() > RT_TEXT_MAX_LIGHTS || sc.ray_depth > RT_TEXT_MAX_DEPTH)
+        return RT_ERR_BAD_SCENE;
+    sc.shading = has_samples ? RT_SHADE_PATH : (has_whitted ? RT_SHADE_WHITTED : RT_SHADE_FLAT);
+    sc.n_prims = (uint32_t)prims.size();
+    sc.n_lights = (uint32_t)lights.size();
+    const size_t bytes = sizeof(rt_text_scene) + prims.size() * sizeof(rt_text_prim) + lights.size() * sizeof(rt_text_light);
+    char *block = static_cast<char *>(std::malloc(bytes));
+    if (!block) return RT_ERR_OOM;
+    rt_text_prim *pp = reinterpret_cast<rt_text_prim *>(block + sizeof(rt_text_scene));
+    rt_text_light *lp = reinterpret_cast<rt_text_light *>(pp + prims.size());
+    if (!prims.empty()) std::memcpy(pp, prims.data(), prims.size() * sizeof(rt_text_prim));
+    if (!lights.empty()) std::memcpy(lp, lights.data(), lights.size() * sizeof(rt_text_light));
+    sc.prims = pp;
+    sc.lights = lp;
+    std::memcpy(block, &sc, sizeof sc);
+    *out = reinterpret_cast<rt_text_scene *>(block);
+    return RT_OK;
+}
+
+void rt_text_scene_free(rt_text_scene *scene) { std::free(scene); }
 
 void rt_host_tonemap_rgb8(const float *rgb_mean, size_t n_pixels, uint8_t *rgb8) {
     const float inv_gamma = 1 / 2.2f;  // image.h:49,63
