@@ -107,3 +107,56 @@ def have_ref_tool():
 def ref_tool(*args):
     """Run oracle/_ref/ref_tool (the harness around the unmodified reference headers)."""
     return subprocess.run([REF_TOOL, *[str(a) for a in args]], check=True, capture_output=True, text=True)
+
+
+# ---- course text scenes: host compilation of csrc/text_core.cuh (PARITY UNPINNED, see oracle/text_oracle.cpp) ----
+TEXT_LIB_PATH = os.path.join(ORACLE_DIR, "libtext_oracle.so")
+_text_lib = None
+
+
+def text_lib():
+    global _text_lib
+    if _text_lib is None:
+        if not os.path.exists(TEXT_LIB_PATH):
+            subprocess.run(["make", "-C", ORACLE_DIR, "oracle", "CC=gcc", "CXX=g++"], check=True, capture_output=True)
+        L = C.CDLL(TEXT_LIB_PATH)
+        L.torc_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                  C.c_void_p, C.c_uint32]
+        L.torc_ids.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.torc_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        L.torc_emitter_solid_angle.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
+        L.torc_emitter_solid_angle.restype = C.c_double
+        _text_lib = L
+    return _text_lib
+
+
+def text_render(scene, width, height, samples, seed=0, sample_begin=0, sample_end=0, n_threads=0):
+    d = scene.desc()
+    out = np.zeros((height, width, 3), np.float32)
+    n_threads = n_threads or min(os.cpu_count() or 1, 16)
+    text_lib().torc_render(C.addressof(d), width, height, samples, sample_begin, sample_end or samples, seed,
+                           out.ctypes.data, n_threads)
+    return out
+
+
+def text_ids(scene, width, height):
+    d = scene.desc()
+    out = np.zeros((height, width), np.int32)
+    text_lib().torc_ids(C.addressof(d), width, height, out.ctypes.data)
+    return out
+
+
+def text_closest(scene, origin, direction, tmin=0.0):
+    """(t, prim, normal[3], inside) of the closest hit of one world-space ray."""
+    d = scene.desc()
+    o = np.asarray(origin, np.float32)
+    dr = np.asarray(direction, np.float32)
+    out = np.zeros(6, np.float32)
+    text_lib().torc_closest(C.addressof(d), o.ctypes.data, dr.ctypes.data, tmin, out.ctypes.data)
+    return float(out[0]), int(out[1]), out[2:5].copy(), bool(out[5])
+
+
+def text_emitter_solid_angle(scene, x, n, seed=1):
+    d = scene.desc()
+    xx = np.asarray(x, np.float32)
+    return text_lib().torc_emitter_solid_angle(C.addressof(d), xx.ctypes.data, n, seed)

@@ -12,7 +12,7 @@ from ._abi import (RT_FLAG_ACCUMULATE, RT_MODE_BEAUTY, RT_MODE_PRIMARY_IDS, rt_r
 LIB_PATH = os.environ.get("RT_GPU_LIB") or os.path.join(_abi.PKG_DIR, "librt_gpu.so")
 
 # every symbol include/rt_gpu.h declares
-SYMBOLS = ["rt_gpu_create", "rt_gpu_destroy", "rt_gpu_upload_scene", "rt_gpu_render", "rt_gpu_readback",
+SYMBOLS = ["rt_gpu_create", "rt_gpu_destroy", "rt_gpu_upload_scene", "rt_gpu_upload_text_scene", "rt_gpu_render", "rt_gpu_readback",
            "rt_gpu_accum_device_ptr", "rt_gpu_readback_rgb8", "rt_gpu_set_profiling", "rt_gpu_fp32_peak", "rt_gpu_last_error",
            "rt_gpu_device_count", "rt_gpu_abi_version"]
 
@@ -27,6 +27,7 @@ def lib():
         L.rt_gpu_destroy.argtypes = [C.c_void_p]
         L.rt_gpu_destroy.restype = None
         L.rt_gpu_upload_scene.argtypes = [C.c_void_p, C.POINTER(rt_scene_desc)]
+        L.rt_gpu_upload_text_scene.argtypes = [C.c_void_p, C.c_void_p]
         L.rt_gpu_render.argtypes = [C.c_void_p, C.POINTER(rt_render_params)]
         L.rt_gpu_readback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(rt_stats)]
         L.rt_gpu_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -82,6 +83,12 @@ class RtGpu:
     def upload_scene(self, scene):
         d = scene.desc()
         _check(lib().rt_gpu_upload_scene(self._h, C.byref(d)), "rt_gpu_upload_scene")
+        self._scene = scene
+
+    def upload_text_scene(self, scene):
+        """Course text scene (textscene.TextScene); render / readback / primary_ids then work on it."""
+        d = scene.desc()
+        _check(lib().rt_gpu_upload_text_scene(self._h, C.byref(d)), "rt_gpu_upload_text_scene")
         self._scene = scene
 
     def set_profiling(self, enable):

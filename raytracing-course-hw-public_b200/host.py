@@ -9,7 +9,7 @@ from ._abi import NODE_DTYPE, BvhData, rt_bvh_build, rt_scene_desc
 
 LIB_PATH = os.path.join(_abi.PKG_DIR, "librt_host.so")
 SYMBOLS = ["rt_scene_save", "rt_scene_load", "rt_scene_free", "rt_scene_validate", "rt_host_build_bvh",
-           "rt_host_free_bvh", "rt_host_tonemap_rgb8", "rt_host_write_ppm"]
+           "rt_host_free_bvh", "rt_host_tonemap_rgb8", "rt_host_write_ppm", "rt_text_scene_parse", "rt_text_scene_free"]
 
 _lib = None
 
