@@ -168,7 +168,7 @@ typedef struct rt_stats {
     uint64_t kernel_launches;  /* kernels launched by the last rt_gpu_render */
 } rt_stats;
 
-/* ---- course text scenes (sample_data/scene-*.txt, homebrew_primitives/*.txt) -------------------------
+/* ---- course text scenes (sample_data scene-NNN.txt, homebrew_primitives) ----------------------------------
  * PARITY UNPINNED: the reference at HEAD cannot load or render these (no parser, triangle-only geometry,
  * no delta lights, no refraction).  The structures follow the file grammar; the
  * semantics are documented in csrc/text_core.cuh.  Scenes are tiny (<= RT_TEXT_MAX_PRIMS primitives), so

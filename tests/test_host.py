@@ -35,7 +35,7 @@ def assert_same_scene(a, b):
 def declared_symbols(header):
     text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rt_(?:gpu|host|scene)_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(rt_(?:gpu|host|scene|text_scene)_\w+)\s*\(", text)))
 
 
 def test_c_abi_exports_every_declared_symbol():
