@@ -249,7 +249,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     def step(i):
         flush.fill_(i & 255)  # L2 flush between iterations
-        sums = rtdist.render_distributed(rt, w, h, spp_total, seed, rank, world, local_rank)
+        sums = rtdist.render_distributed(rt, w, h, spp_total, seed, rank, world, local_rank, args.paths)
         return sums
 
     for i in range(args.warmup):
@@ -286,7 +286,7 @@ def run_gpu_arm(args, rank, world, local_rank):
 
     def e2e_step():
         rt.upload_scene(scene)  # host re-pack + H2D of the whole scene
-        sums = rtdist.render_distributed(rt, w, h, spp_total, seed, rank, world, local_rank)
+        sums = rtdist.render_distributed(rt, w, h, spp_total, seed, rank, world, local_rank, args.paths)
         if rank == 0:
             rt.readback_into(host_out)  # D2H of the per-pixel sums, / spp on the host
         return sums
@@ -308,7 +308,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         rt.set_profiling(True)
         sb, se = rtdist.sample_range(spp_total, rank, world)
-        rt.render(w, h, spp_total, seed=seed, sample_begin=sb, sample_end=se)
+        rt.render(w, h, spp_total, seed=seed, sample_begin=sb, sample_end=se, max_paths_in_flight=args.paths)
         pst = rt.stats()
         rt.set_profiling(False)
         kernel_ms = {"generate": pst["kernel_ms"][0], "extend": pst["kernel_ms"][1], "shade": pst["kernel_ms"][2],
@@ -368,6 +368,7 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp", type=int, default=SPP_PER_GPU, help="samples per pixel per GPU")
+    ap.add_argument("--paths", type=int, default=0, help="paths in flight per batch (0 = library default)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
     _capture_stdout()

@@ -150,7 +150,7 @@ typedef struct rt_render_params {
     uint32_t sample_end;     /* 0 => samples */
     uint32_t mode;           /* rt_render_mode */
     uint64_t seed;           /* Philox key */
-    uint32_t max_paths_in_flight; /* 0 => default (8 Mi) */
+    uint32_t max_paths_in_flight; /* 0 => default (128 Mi paths, at most half of the free device memory) */
     uint32_t flags;          /* RT_FLAG_* */
 } rt_render_params;
 

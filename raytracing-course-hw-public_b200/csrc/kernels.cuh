@@ -146,7 +146,15 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 
 __device__ __forceinline__ bool link_is_leaf(int32_t link) { return link < 0 && link != kLinkDone && link != kLinkPop; }
 
-__global__ void __launch_bounds__(kExtendThreads) k_extend(DBvh bvh, float eps, Queues q, uint32_t bounce) {
+#ifndef RT_EXT_MINB
+#define RT_EXT_MINB 0  // minimum resident CTAs per SM asked of the compiler (0: let it choose)
+#endif
+#if RT_EXT_MINB
+__global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB) k_extend(
+#else
+__global__ void __launch_bounds__(kExtendThreads) k_extend(
+#endif
+    DBvh bvh, float eps, Queues q, uint32_t bounce) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
     const float4 *__restrict__ qo = q.o[bounce & 1];
@@ -395,7 +403,15 @@ __device__ __forceinline__ float light_pdf_warp(const DScene &s, bool active, f3
     return sum / static_cast<float>(s.n_lights);
 }
 
-__global__ void __launch_bounds__(kShadeThreads) k_shade(DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q,
+#ifndef RT_SHADE_MINB
+#define RT_SHADE_MINB 0
+#endif
+#if RT_SHADE_MINB
+__global__ void __launch_bounds__(kShadeThreads, RT_SHADE_MINB) k_shade(
+#else
+__global__ void __launch_bounds__(kShadeThreads) k_shade(
+#endif
+    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q,
                                                         uint32_t bounce) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];

@@ -45,11 +45,12 @@ def reduce_sums(tensor, dst=0):
     return tensor
 
 
-def render_distributed(rt, width, height, samples, seed, rank, world, device_index):
+def render_distributed(rt, width, height, samples, seed, rank, world, device_index, max_paths_in_flight=0):
     """Render this rank's sample range on its GPU, reduce to rank 0. Returns the torch view of the sums
     (complete on rank 0 only)."""
     sb, se = sample_range(samples, rank, world)
-    rt.render(width, height, samples, seed=seed, sample_begin=sb, sample_end=max(se, sb))
+    rt.render(width, height, samples, seed=seed, sample_begin=sb, sample_end=max(se, sb),
+              max_paths_in_flight=max_paths_in_flight)
     t = accum_as_tensor(rt, device_index)
     return reduce_sums(t, 0)
 
