@@ -10,7 +10,8 @@
 // Path state is SoA of float4 (128-bit coalesced loads/stores), ping-ponged between queue b and b+1:
 //   q_o   = (origin.xyz,     pixel index bits)
 //   q_d   = (direction.xyz,  sample index bits)
-//   q_thr = (throughput.rgb, unused)
+//   q_thr = (throughput.rgb [x f_cos when pending], p_partial >= 0 when the path's pdf still needs the light
+//            pdf of this ray ("pending", also bit 31 of the sample index), else -1)
 //   hit   = (t, beta, gamma, BVH-order triangle index bits or -1)      written by extend, read by shade
 //   rad   = per-path radiance accumulator, indexed by the path's fixed slot (no atomics: one owner)
 // extend and shade are persistent: grid = SMs x resident CTAs, each warp pulls 32 queue entries at a
@@ -43,6 +44,7 @@ struct Queues {
     uint32_t *fetch_ext;    // [ray_depth] work-fetch cursors of k_extend
     uint32_t *fetch_shade;  // [ray_depth] work-fetch cursors of k_shade
     unsigned long long *stats;  // [4] extension rays, light pdf rays, shades, samples
+    float *lpdf;                // light pdf of the queued ray (bvh_mix_dist::pdf), written by k_extend for pending paths
 };
 
 constexpr int kExtendThreads = 128;
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
     const f3 dir = camera_dir(cam, static_cast<float>(px) + jx, static_cast<float>(py) + jy);
     q.o[0][slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel));
     q.d[0][slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample));
-    q.thr[0][slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    q.thr[0][slot] = make_float4(1.0f, 1.0f, 1.0f, -1.0f);
     q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
@@ -111,9 +113,8 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
 // are those of closest_hit() in pt_core.cuh, so both give the same hit.
 //
 // Compile-time knobs (A/B-tested on the B200, DESIGN.md "k_extend"; defaults = the fastest measured):
-#ifndef RT_EXT_QNODE
-#define RT_EXT_QNODE 1        // 1: 32-byte quantised nodes (one sector per visit)  0: 64-byte full-precision DNodes
-#endif
+// (64-byte full-precision nodes were the other candidate: equal within 4 % once the kernel was issue-bound, and
+// slower with the SAH tree; removed.)
 #ifndef RT_EXT_SMEM_STACK
 #define RT_EXT_SMEM_STACK 16  // traversal-stack entries per thread kept in shared memory (0: all in local memory)
 #endif
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB) k_extend(
 #else
 __global__ void __launch_bounds__(kExtendThreads) k_extend(
 #endif
-    DBvh bvh, float eps, Queues q, uint32_t bounce) {
+    DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce) {
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
     const float4 *__restrict__ qo = q.o[bounce & 1];
@@ -175,15 +176,33 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1), ood = mk3(0, 0, 0);
     float best_t = INFINITY, best_b = 0.0f, best_c = 0.0f;
     int32_t best_tri = -1;
+    // A pending ray (bit 31 of its sample index) is traversed twice: first through the light BVH, all hits, summing
+    // bvh_mix_dist::pdf (raytracer.h:363-375) into lsum (best_t stays +inf, so nothing is culled), then through the
+    // scene BVH for the closest hit.  Both run in the same warp-synchronous loops, so the light-pdf traversals get
+    // this kernel's lane occupancy and refill instead of k_shade's (7 of 32 lanes, 57 % of its instructions).
+    bool lmode = false;
+    float lsum = 0.0f;
+    const QNode *node_base = bvh.qnodes;
+    const DTri *tri_base = bvh.tris;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes ---------------------------------------------------
-        const bool idle = link == kLinkDone && leaf == 0;
+        bool idle = link == kLinkDone && leaf == 0;
         if (idle && ray != kNoRay) {
-            q.hit[ray] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
-            ray = kNoRay;
+            if (lmode) {  // light pdf done: now the closest hit of the same ray
+                q.lpdf[ray] = lsum * inv_n_lights;
+                lmode = false;
+                node_base = bvh.qnodes;
+                tri_base = bvh.tris;
+                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
+                idle = link == kLinkDone;
+            }
+            if (idle) {
+                q.hit[ray] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
+                ray = kNoRay;
+            }
         }
         const uint32_t m_idle = __ballot_sync(FULL, idle);
         if (m_idle) {
@@ -213,7 +232,18 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 best_b = best_c = 0.0f;
                 best_tri = -1;
                 sp = 0;
-                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;  // a leaf root is postponed below
+                lmode = (__float_as_uint(d4.w) >> 31) != 0u && lbvh.root != RT_LINK_NONE;
+                lsum = 0.0f;
+                if (lmode) {
+                    node_base = lbvh.qnodes;
+                    tri_base = lbvh.tris;
+                    link = lbvh.root;
+                } else {
+                    if (__float_as_uint(d4.w) >> 31) q.lpdf[ray] = 0.0f;  // pending, but the scene has no light BVH
+                    node_base = bvh.qnodes;
+                    tri_base = bvh.tris;
+                    link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;  // a leaf root is postponed below
+                }
             }
             pool_next += take;
             if (avail == 0 && m_idle == FULL) break;  // queue drained and nothing in flight
@@ -246,6 +276,14 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                     link = t < best_t ? l : kLinkPop;
                 }
             }
+            // (1b) a pending ray whose light-BVH traversal is complete starts its scene traversal at once
+            if (lmode && link == kLinkDone && leaf == 0) {
+                q.lpdf[ray] = lsum * inv_n_lights;
+                lmode = false;
+                node_base = bvh.qnodes;
+                tri_base = bvh.tris;
+                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
+            }
             // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
             if (leaf == 0 && link_is_leaf(link)) {
                 leaf = link;
@@ -263,31 +301,12 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             }
             // (4) at most one node step
             if (link >= 0) {
-#if RT_EXT_QNODE
-                const f8 nq = ld8(bvh.qnodes + link);  // 32 B quantised node = one sector, one 256-bit load
+                const f8 nq = ld8(node_base + link);  // 32 B quantised node = one sector, one 256-bit load
                 const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood,
                                                eps, best_t);
                 const bool hl = nt.hl, hr = nt.hr;
                 const float dl = nt.dl, dr = nt.dr;
                 const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
-#else
-                const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
-                const f8 na = ld8(p), nb = ld8(p + 32);  // 64 B node = two 256-bit loads
-                // slab test of both children (bvh.h:137-152) in fused form t = plane * (1/d) - o/d; the
-                // interval is clipped to [eps, best_t] inside the min/max chain (hit <=> lo <= hi)
-                const float lx0 = fmaf(na.a, idir.x, -ood.x), lx1 = fmaf(na.d, idir.x, -ood.x);
-                const float ly0 = fmaf(na.b, idir.y, -ood.y), ly1 = fmaf(na.e, idir.y, -ood.y);
-                const float lz0 = fmaf(na.c, idir.z, -ood.z), lz1 = fmaf(na.f, idir.z, -ood.z);
-                const float rx0 = fmaf(na.g, idir.x, -ood.x), rx1 = fmaf(nb.b, idir.x, -ood.x);
-                const float ry0 = fmaf(na.h, idir.y, -ood.y), ry1 = fmaf(nb.c, idir.y, -ood.y);
-                const float rz0 = fmaf(nb.a, idir.z, -ood.z), rz1 = fmaf(nb.d, idir.z, -ood.z);
-                const float dl = fmaxf(fmax3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), eps);
-                const float el = fminf(fmin3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1)), best_t);
-                const float dr = fmaxf(fmax3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), eps);
-                const float er = fminf(fmin3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1)), best_t);
-                const bool hl = dl <= el, hr = dr <= er;
-                const int32_t ll = static_cast<int32_t>(f2u(nb.e)), lr = static_cast<int32_t>(f2u(nb.f));
-#endif
                 // near child first; ties go left (bvh.h:216-219)
                 const bool right_first = hr && (!hl || dl > dr);
                 if (hl && hr) {
@@ -311,7 +330,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             bool more = leaf != 0;
             while (__any_sync(FULL, more)) {
                 if (more) {
-                    const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+                    const char *p = reinterpret_cast<const char *>(tri_base + k);
                     const f8 ta = ld8(p);
                     const f4 t2 = ld4(p + 32);
                     const f4 t0 = f4{ta.a, ta.b, ta.c, ta.d}, t1 = f4{ta.e, ta.f, ta.g, ta.h};
@@ -324,10 +343,18 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                     const float inv = rcp_rn(-dot(d, n));
                     const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
                     if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < best_t) {
-                        best_t = t;
-                        best_b = beta;
-                        best_c = gamma;
-                        best_tri = static_cast<int32_t>(k);
+                        if (lmode) {  // every hit counts, occluded or not, both faces (raytracer.h:79-84,255-261)
+                            const f4 le = ld4(light_extra + k);
+                            const f3 xy = d * t;  // y - x
+                            const float d2 = len2(xy);
+                            const f3 w = xy * rsqrtf(d2);
+                            lsum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);
+                        } else {
+                            best_t = t;
+                            best_b = beta;
+                            best_c = gamma;
+                            best_tri = static_cast<int32_t>(k);
+                        }
                     }
                     more = !(f2u(t0.w) & RT_LAST_BIT);
                     ++k;
@@ -336,73 +363,17 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             leaf = 0;  // a lane that waited with a second leaf postpones it in step (2) of the next inner phase
         }
     }
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(q.stats + 0, static_cast<unsigned long long>(count));
 }
 
-// bvh_mix_dist::pdf (raytracer.h:363-375) for all 32 lanes as one warp-synchronous loop: every iteration
-// a lane either takes one inner-node step of the light BVH or tests one triangle (a leaf in progress is
-// carried as the link ~next_triangle), and the loop ends on a warp vote.  The per-thread light_pdf() of
-// pt_core.cuh ran with 2-5 of 32 lanes active inside k_shade; this keeps the lanes converged.
-__device__ __forceinline__ float light_pdf_warp(const DScene &s, bool active, f3 x, f3 dir) {
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const DBvh &bvh = s.light;
-    int32_t stack[RT_STACK_SIZE];
-    int sp = 0;
-    int32_t link = (active && bvh.root != RT_LINK_NONE) ? bvh.root : kLinkDone;
-    const f3 idir = mk3(rcp_rn(dir.x), rcp_rn(dir.y), rcp_rn(dir.z));
-    const f3 ood = mk3(x.x * idir.x, x.y * idir.y, x.z * idir.z);
-    float sum = 0.0f;
-    while (__any_sync(FULL, link != kLinkDone)) {
-        if (link >= 0) {
-            const char *p = reinterpret_cast<const char *>(bvh.nodes + link);
-            const f8 na = ld8(p), nb = ld8(p + 32);
-            const float lx0 = fmaf(na.a, idir.x, -ood.x), lx1 = fmaf(na.d, idir.x, -ood.x);
-            const float ly0 = fmaf(na.b, idir.y, -ood.y), ly1 = fmaf(na.e, idir.y, -ood.y);
-            const float lz0 = fmaf(na.c, idir.z, -ood.z), lz1 = fmaf(na.f, idir.z, -ood.z);
-            const float rx0 = fmaf(na.g, idir.x, -ood.x), rx1 = fmaf(nb.b, idir.x, -ood.x);
-            const float ry0 = fmaf(na.h, idir.y, -ood.y), ry1 = fmaf(nb.c, idir.y, -ood.y);
-            const float rz0 = fmaf(nb.a, idir.z, -ood.z), rz1 = fmaf(nb.d, idir.z, -ood.z);
-            // all-hit traversal: a box is entered iff t_min <= t_max && t_max >= eps (bvh.h:147), no upper bound
-            const bool hl = fmaxf(fmax3(fminf(lx0, lx1), fminf(ly0, ly1), fminf(lz0, lz1)), s.eps) <=
-                            fmin3(fmaxf(lx0, lx1), fmaxf(ly0, ly1), fmaxf(lz0, lz1));
-            const bool hr = fmaxf(fmax3(fminf(rx0, rx1), fminf(ry0, ry1), fminf(rz0, rz1)), s.eps) <=
-                            fmin3(fmaxf(rx0, rx1), fmaxf(ry0, ry1), fmaxf(rz0, rz1));
-            const int32_t ll = static_cast<int32_t>(f2u(nb.e)), lr = static_cast<int32_t>(f2u(nb.f));
-            if (hl && hr) {
-                stack[sp++] = lr;
-                link = ll;
-            } else if (hl || hr) {
-                link = hl ? ll : lr;
-            } else {
-                link = sp > 0 ? stack[--sp] : kLinkDone;
-            }
-        } else if (link != kLinkDone) {
-            const uint32_t k = static_cast<uint32_t>(~link);
-            const char *p = reinterpret_cast<const char *>(bvh.tris + k);
-            const f8 ta = ld8(p);
-            const f4 t2 = ld4(p + 32);
-            const f3 e1 = mk3(ta.e, ta.f, ta.g), e2 = mk3(t2.x, t2.y, t2.z);
-            const f3 n = cross(e1, e2);
-            const f3 y = x - mk3(ta.a, ta.b, ta.c);
-            const f3 r = cross(dir, y);
-            const float inv = rcp_rn(-dot(dir, n));
-            const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
-            if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= s.eps) {
-                const f4 le = ld4(s.light_extra + k);
-                const f3 xy = dir * t;  // y - x
-                const float d2 = len2(xy);
-                const f3 w = xy * rsqrtf(d2);
-                sum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);  // raytracer.h:79-84,255-261
-            }
-            if (f2u(ta.d) & RT_LAST_BIT)
-                link = sp > 0 ? stack[--sp] : kLinkDone;
-            else
-                link = ~static_cast<int32_t>(k + 1);  // next triangle of the same leaf
-        }
-    }
-    return sum / static_cast<float>(s.n_lights);
-}
-
+// k_shade, bounce b.  For every entry of queue b:
+//   1. if the path is pending (its previous bounce sampled a direction and the scene has lights): resolve that
+//      bounce with the light pdf k_extend summed along this very ray — p = p_partial + (1 - VNDF_factor)/2 * lpdf,
+//      p < EPS ends the path, else throughput = (thr * f_cos) / p  (shade_resolve, raytracer.h:572-590);
+//   2. shade_begin: miss -> background; hit data; alpha coin; emission; strategy coin; direction sample;
+//   3. shade_weights of the sampled direction (BRDF * cos, VNDF and cosine pdfs); without lights the bounce is
+//      resolved at once, with lights the entry goes out pending;
+//   4. survivors are compacted into queue b+1 with a warp-aggregated append.
+// The light-pdf traversal itself lives in k_extend (second traversal mode of a pending ray).
 #ifndef RT_SHADE_MINB
 #define RT_SHADE_MINB 0
 #endif
@@ -411,80 +382,91 @@ __global__ void __launch_bounds__(kShadeThreads, RT_SHADE_MINB) k_shade(
 #else
 __global__ void __launch_bounds__(kShadeThreads) k_shade(
 #endif
-    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q,
-                                                        uint32_t bounce) {
+    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q, uint32_t bounce) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
     const uint32_t count = q.count[bounce];
     const int in = bounce & 1, out = in ^ 1;
     const bool last = bounce + 1 == s.ray_depth;
-    uint32_t n_light = 0, n_shade = 0;
+    uint32_t n_light = 0, n_shade = 0, n_ext = 0;
     for (;;) {
         const uint32_t i = warp_fetch(q.fetch_shade + bounce);
         if (i - lane_id() >= count) break;
         bool alive = false;
         f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(0, 0, 0), rad = mk3(0, 0, 0);
+        float pending = -1.0f;
         uint32_t pixel = 0, sample = 0;
-        ShadeMid mid;
-        mid.pos = mid.dir = mk3(0, 0, 1);
-        ShadeStep step = SHADE_END;
         if (i < count) {
             const float4 o4 = q.o[in][i], d4 = q.d[in][i], t4 = q.thr[in][i], h4 = q.hit[i];
             o = mk3(o4.x, o4.y, o4.z);
             d = mk3(d4.x, d4.y, d4.z);
             thr = mk3(t4.x, t4.y, t4.z);
             pixel = __float_as_uint(o4.w);
-            sample = __float_as_uint(d4.w);
-            Hit h;
-            h.t = h4.x;
-            h.b = h4.y;
-            h.c = h4.z;
-            h.tri = __float_as_int(h4.w);
-            const RngKey key{pixel, sample, bp.k0, bp.k1};
-            n_shade += h.tri >= 0 ? 1u : 0u;
-            step = shade_begin(s, lut, key, bounce, last, h, o, d, thr, rad, mid);
-            alive = step == SHADE_PASS;
-        }
-        // light pdf of every sampled direction, lanes converged (skipped entirely for scenes without lights)
-        float p_light = 0.0f;
-        if (s.n_lights > 0) {
-            p_light = light_pdf_warp(s, step == SHADE_SAMPLED, mid.pos, mid.dir);
-            n_light += step == SHADE_SAMPLED ? 1u : 0u;
-        }
-        if (step == SHADE_SAMPLED) alive = shade_finish(s, mid, p_light, o, d, thr);
-        if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f) {  // NaN != 0 is true: poisons the sample like the reference
-            const uint32_t slot = (sample - bp.s0) * bp.npix + (pixel - bp.pix0);
-            float4 acc = q.rad[slot];
-            acc.x += rad.x;
-            acc.y += rad.y;
-            acc.z += rad.z;
-            q.rad[slot] = acc;
+            sample = __float_as_uint(d4.w) & 0x7FFFFFFFu;
+            bool live = true;
+            if (__float_as_uint(d4.w) >> 31) live = shade_resolve(s, thr, t4.w, q.lpdf[i], thr);  // previous bounce
+            if (live) {
+                ++n_ext;  // this extension ray's hit is consumed (cast_ray of the reference)
+                Hit h;
+                h.t = h4.x;
+                h.b = h4.y;
+                h.c = h4.z;
+                h.tri = __float_as_int(h4.w);
+                const RngKey key{pixel, sample, bp.k0, bp.k1};
+                n_shade += h.tri >= 0 ? 1u : 0u;
+                ShadeMid mid;
+                const f3 d_in = d;
+                const ShadeStep step = shade_begin(s, lut, key, bounce, last, h, o, d, thr, rad, mid);
+                alive = step == SHADE_PASS;
+                if (step == SHADE_SAMPLED) {
+                    n_light += s.n_lights > 0 ? 1u : 0u;  // bvh_mix_dist::pdf calls of the reference (raytracer.h:573)
+                    const ShadeWeights w = shade_weights(s, mid, d_in);
+                    if (len2(w.f_cos) != 0.0f) {  // raytracer.h:584-586
+                        if (s.n_lights > 0) {  // resolved by the next k_shade with the light pdf of (pos, dir)
+                            thr = thr * w.f_cos;
+                            pending = w.p_partial;
+                            alive = true;
+                        } else {
+                            alive = shade_resolve(s, thr * w.f_cos, w.p_partial, 0.0f, thr);
+                        }
+                        o = mid.pos;
+                        d = mid.dir;
+                    }
+                }
+                if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f) {  // NaN != 0 is true: poisons the sample like the reference
+                    const uint32_t slot = (sample - bp.s0) * bp.npix + (pixel - bp.pix0);
+                    float4 acc = q.rad[slot];
+                    acc.x += rad.x;
+                    acc.y += rad.y;
+                    acc.z += rad.z;
+                    q.rad[slot] = acc;
+                }
+            }
         }
         const uint32_t dst = warp_append(q.count + bounce + 1, alive);
         if (alive) {
             q.o[out][dst] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-            q.d[out][dst] = make_float4(d.x, d.y, d.z, __uint_as_float(sample));
-            q.thr[out][dst] = make_float4(thr.x, thr.y, thr.z, 0.0f);
+            q.d[out][dst] = make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u)));
+            q.thr[out][dst] = make_float4(thr.x, thr.y, thr.z, pending);
         }
     }
-    // block-level reduction of the work counters -> one atomic per CTA
-    __shared__ uint32_t s_cnt[2];
-    if (threadIdx.x == 0) s_cnt[0] = s_cnt[1] = 0;
+    // block-level reduction of the work counters -> one atomic per CTA and counter
+    __shared__ uint32_t s_cnt[3];
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int off = 16; off > 0; off >>= 1) {
         n_light += __shfl_down_sync(0xFFFFFFFFu, n_light, off);
         n_shade += __shfl_down_sync(0xFFFFFFFFu, n_shade, off);
+        n_ext += __shfl_down_sync(0xFFFFFFFFu, n_ext, off);
     }
     if (lane_id() == 0) {
-        atomicAdd(&s_cnt[0], n_light);
-        atomicAdd(&s_cnt[1], n_shade);
+        atomicAdd(&s_cnt[0], n_ext);
+        atomicAdd(&s_cnt[1], n_light);
+        atomicAdd(&s_cnt[2], n_shade);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_cnt[0]) atomicAdd(q.stats + 1, static_cast<unsigned long long>(s_cnt[0]));
-        if (s_cnt[1]) atomicAdd(q.stats + 2, static_cast<unsigned long long>(s_cnt[1]));
-    }
+    if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(q.stats + threadIdx.x, static_cast<unsigned long long>(s_cnt[threadIdx.x]));
 }
 
 // accum[pixel] += sum_j sanitize(rad[j * npix + p])  — fixed order, deterministic, no atomics

@@ -608,7 +608,7 @@ RT_HD float cosine_pdf(f3 ng, f3 dir) { return fmaxf(dot(ng, dir) * RT_INV_PI, 0
 RT_HD f3 light_sample(const DScene &s, f3 x, float u_index, float u, float v) {
     uint32_t k = static_cast<uint32_t>(u_index * static_cast<float>(s.n_lights));
     k = k < s.n_lights ? k : s.n_lights - 1;
-    const char *p = reinterpret_cast<const char *>(s.light.tris + k);
+    const char *p = reinterpret_cast<const char *>(s.light_sample + k);
     const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
     if (u + v > 1.0f) {
         u = 1.0f - u;
@@ -706,17 +706,44 @@ RT_HD ShadeStep shade_begin(const DScene &s, const float *lut, const RngKey &key
     return SHADE_SAMPLED;
 }
 
-// Second half: pdf mixture, BRDF, throughput (raytracer.h:572-590). `p_light` = bvh_mix_dist::pdf of
-// (mid.pos, mid.dir), ignored when the scene has no lights. Returns true when the path continues.
+// Second half: pdf mixture, BRDF, throughput (raytracer.h:572-590), in two steps so that the wavefront can
+// obtain the light pdf of (mid.pos, mid.dir) from the traversal kernel between them:
+//   shade_weights: everything that does not need the light pdf
+//        f_cos     = pbr_brdf * max(0, dir . Ns)
+//        p_partial = VNDF_factor * p_vndf + (1 - VNDF_factor) * p_cos * (1/2 with lights, 1 without)
+//   shade_resolve: p = p_partial + (1 - VNDF_factor)/2 * p_light;  p < EPS -> the path ends (raytracer.h:576-578);
+//        scl = f_cos / p;  |scl|^2 == 0 -> ends (raytracer.h:584-586);  thr *= scl.
+// Same terms as the reference's `pbr_brdf * (max(0, cos) / p)` with p = 1/3 p_vndf + 2/3 (p_cos + p_light)/2, summed
+// in a different order (differences of a few ulp).
+struct ShadeWeights {
+    f3 f_cos;
+    float p_partial;
+};
+RT_HD ShadeWeights shade_weights(const DScene &s, const ShadeMid &mid, f3 d_in) {
+    ShadeWeights w;
+    const float p_vndf = vndf_pdf(mid.alpha, s.eps, d_in, mid.sf.ns, mid.dir);
+    const float p_cos = cosine_pdf(mid.sf.ng, mid.dir);
+    const float k = s.n_lights > 0 ? 0.5f : 1.0f;  // mix_dist::pdf = mean of the sub-pdfs, raytracer.h:395-407
+    w.p_partial = s.vndf_factor * p_vndf + (1.0f - s.vndf_factor) * k * p_cos;
+    w.f_cos = pbr_brdf(mid.sf, mid.alpha, d_in, mid.dir) * fmaxf(0.0f, dot(mid.dir, mid.sf.ns));
+    return w;
+}
+RT_HD float light_pdf_weight(const DScene &s) { return s.n_lights > 0 ? (1.0f - s.vndf_factor) * 0.5f : 0.0f; }
+
+// thr_f = throughput * f_cos.  Returns false when the path ends; else thr = thr_f / p.
+RT_HD bool shade_resolve(const DScene &s, f3 thr_f, float p_partial, float p_light, f3 &thr) {
+    const float p = p_partial + light_pdf_weight(s) * p_light;
+    if (p < s.eps) return false;  // NaN p continues, like the reference
+    const f3 scaled = thr_f * (1.0f / p);
+    if (len2(scaled) == 0.0f) return false;
+    thr = scaled;
+    return true;
+}
+
 RT_HD bool shade_finish(const DScene &s, const ShadeMid &mid, float p_light, f3 &o, f3 &d, f3 &thr) {
-    const float p_vndf = vndf_pdf(mid.alpha, s.eps, d, mid.sf.ns, mid.dir);
-    float p_mis = cosine_pdf(mid.sf.ng, mid.dir);
-    if (s.n_lights > 0) p_mis = (p_mis + p_light) * 0.5f;  // mix_dist::pdf = mean of the sub-pdfs, raytracer.h:395-407
-    const float p = s.vndf_factor * p_vndf + (1.0f - s.vndf_factor) * p_mis;
-    if (p < s.eps) return false;  // raytracer.h:576-578 (NaN p continues, like the reference)
-    const f3 scl = pbr_brdf(mid.sf, mid.alpha, d, mid.dir) * (fmaxf(0.0f, dot(mid.dir, mid.sf.ns)) / p);
-    if (len2(scl) == 0.0f) return false;  // raytracer.h:584-586
-    thr = thr * scl;
+    const ShadeWeights w = shade_weights(s, mid, d);
+    if (len2(w.f_cos) == 0.0f) return false;  // raytracer.h:584-586 (decidable before the light pdf is known)
+    if (!shade_resolve(s, thr * w.f_cos, w.p_partial, p_light, thr)) return false;
     o = mid.pos;
     d = mid.dir;
     return true;

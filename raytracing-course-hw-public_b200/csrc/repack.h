@@ -30,6 +30,7 @@ struct PackedScene {
     std::vector<DAttr> attrs;
     std::vector<DTangent> tangents;  // empty when every tangent is (1,0,0)
     std::vector<DLight> light_extra;
+    std::vector<DTri> light_sample;  // emissive triangles in the host light BVH's object order (sampling order)
     std::vector<DMat> materials;
     std::vector<DTex> textures;
     std::vector<uint32_t> texels;
@@ -219,7 +220,19 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
     } else if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene)) {
         return rc;
     }
-    if (int rc = pack_bvh(sc, sc.light_bvh, out.light)) return rc;
+    // light BVH: the traversal (all-hit light pdf) uses a rebuilt tree as well; the sampling list keeps the host's order
+    {
+        PackedBvh host_order;
+        if (int rc = pack_bvh(sc, sc.light_bvh, host_order)) return rc;
+        out.light_sample = host_order.tris;
+        if (rebuild_scene_bvh && sc.light_bvh.n_objects > 0 && sc.light_bvh.root != RT_NO_CHILD) {
+            BuiltBvh built;
+            build_sah_bvh(sc.tri_pos, sc.light_bvh.objects, sc.light_bvh.n_objects, built);
+            if (int rc = pack_bvh(sc, built.desc(), out.light)) return rc;
+        } else {
+            out.light = host_order;
+        }
+    }
 
     const uint32_t n = static_cast<uint32_t>(out.scene.order.size());  // device triangle order = packed BVH order
     out.attrs.resize(n);

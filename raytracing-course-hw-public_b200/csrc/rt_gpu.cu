@@ -96,7 +96,7 @@ template <class T> struct DevBuf {
     }
 };
 
-constexpr size_t kBytesPerPath = 8 * sizeof(float4);  // q_o, q_d, q_thr (x2 parities) + hit + rad
+constexpr size_t kBytesPerPath = 8 * sizeof(float4) + sizeof(float);  // q_o, q_d, q_thr (x2 parities) + hit + rad + lpdf
 
 enum KernelKind { K_GENERATE = 0, K_EXTEND = 1, K_SHADE = 2, K_ACCUMULATE = 3, K_IDS = 4, K_COUNT = 8 };
 
@@ -106,10 +106,8 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
     // scene
-    DevBuf<QNode> qnodes;  // scene BVH, quantised (k_extend)
-    DevBuf<DNode> nodes;   // scene BVH, full precision (only in RT_EXT_QNODE=0 builds)
-    DevBuf<DNode> lnodes;  // light BVH, full precision (k_shade's light-pdf traversal)
-    DevBuf<DTri> tris, ltris;
+    DevBuf<QNode> qnodes, lqnodes;  // scene BVH and light BVH, quantised (both traversed by k_extend)
+    DevBuf<DTri> tris, ltris, lsample;
     DevBuf<DAttr> attrs;
     DevBuf<DTangent> tangents;
     DevBuf<DLight> light_extra;
@@ -126,6 +124,7 @@ struct DeviceState {
     rt_camera tcamera;
     // render state
     DevBuf<float4> qo[2], qd[2], qthr[2], hit, rad, accum;
+    DevBuf<float> lpdf;
     DevBuf<uint32_t> counters;
     DevBuf<unsigned long long> stats;
     DevBuf<int32_t> prim_ids;
@@ -162,14 +161,11 @@ namespace {
 
 int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p) {
     CU_CHECK(cudaSetDevice(d.device));
-#if RT_EXT_QNODE
     if (int rc = d.qnodes.upload(p.scene.qnodes, d.stream)) return rc;
-#else
-    if (int rc = d.nodes.upload(p.scene.nodes, d.stream)) return rc;
-#endif
+    if (int rc = d.lqnodes.upload(p.light.qnodes, d.stream)) return rc;
     if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
-    if (int rc = d.lnodes.upload(p.light.nodes, d.stream)) return rc;
     if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
+    if (int rc = d.lsample.upload(p.light_sample, d.stream)) return rc;
     if (int rc = d.attrs.upload(p.attrs, d.stream)) return rc;
     if (int rc = d.tangents.upload(p.tangents, d.stream)) return rc;
     if (int rc = d.light_extra.upload(p.light_extra, d.stream)) return rc;
@@ -179,12 +175,13 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     std::vector<float> lut(p.gamma_lut, p.gamma_lut + 256);
     if (int rc = d.lut.upload(lut, d.stream)) return rc;
     rt::fill_scene_constants(sc, p, d.scene);
-    d.scene.scene.nodes = d.nodes.p;  // null unless RT_EXT_QNODE=0: the device traverses the quantised copy
+    d.scene.scene.nodes = nullptr;  // the device traverses the quantised copies only
     d.scene.scene.qnodes = d.qnodes.p;
     d.scene.scene.tris = d.tris.p;
-    d.scene.light.nodes = d.lnodes.p;
-    d.scene.light.qnodes = nullptr;
+    d.scene.light.nodes = nullptr;
+    d.scene.light.qnodes = d.lqnodes.p;
     d.scene.light.tris = d.ltris.p;
+    d.scene.light_sample = d.lsample.p;
     d.scene.attrs = d.attrs.p;
     d.scene.tangents = p.tangents.empty() ? nullptr : d.tangents.p;
     d.scene.light_extra = d.light_extra.p;
@@ -318,6 +315,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     }
     if (int rc = d.hit.alloc(cap)) return rc;
     if (int rc = d.rad.alloc(cap)) return rc;
+    if (int rc = d.lpdf.alloc(cap)) return rc;
     const uint32_t qdepth = std::max(depth, 1u);
     const size_t n_counters = 3 * static_cast<size_t>(qdepth) + 1;
     if (int rc = d.counters.alloc(n_counters)) return rc;
@@ -334,7 +332,9 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     q.fetch_ext = d.counters.p + qdepth + 1;
     q.fetch_shade = d.counters.p + 2 * qdepth + 1;
     q.stats = d.stats.p;
+    q.lpdf = d.lpdf.p;
 
+    const float inv_n_lights = d.scene.n_lights ? 1.0f / static_cast<float>(d.scene.n_lights) : 0.0f;
     rt::BatchParams bp;
     bp.width = W;
     bp.height = H;
@@ -357,7 +357,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
             rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q);
             mark(ctx, d, K_GENERATE);
             if (ids_mode) {  // pixel-centre rays through the same traversal kernel, then hit -> scene.objects id
-                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.eps, q, 0);
+                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, 0);
                 mark(ctx, d, K_EXTEND);
                 rt::k_ids_from_hits<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.hit.p, d.scene.scene.tris, d.prim_ids.p);
                 mark(ctx, d, K_IDS);
@@ -365,7 +365,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
                 continue;
             }
             for (uint32_t b = 0; b < depth; ++b) {
-                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.eps, q, b);
+                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b);
                 mark(ctx, d, K_EXTEND);
                 rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b);
                 mark(ctx, d, K_SHADE);
@@ -449,7 +449,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        d.qnodes.release(); d.nodes.release(); d.lnodes.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.attrs.release();
+        d.qnodes.release(); d.lqnodes.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }

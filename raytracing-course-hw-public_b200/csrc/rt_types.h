@@ -107,6 +107,9 @@ struct DScene {
     const DAttr *attrs;         // scene-BVH order
     const DTangent *tangents;   // scene-BVH order or nullptr
     const DLight *light_extra;  // light-BVH order
+    const DTri *light_sample;   // emissive triangles in the HOST light BVH's object order: bvh_mix_dist::sample
+                                // draws a uniform index into that list (raytracer.h:355-361), so the sampling
+                                // order stays the reference's even when the light BVH itself is rebuilt
     const DMat *materials;
     const DTex *textures;
     const uint32_t *texels;

@@ -30,6 +30,7 @@ int build(const rt_scene_desc *sc, HostScene &hs) {
     hs.d.scene.tris = hs.p.scene.tris.data();
     hs.d.light.nodes = hs.p.light.nodes.data();
     hs.d.light.tris = hs.p.light.tris.data();
+    hs.d.light_sample = hs.p.light_sample.data();
     hs.d.attrs = hs.p.attrs.data();
     hs.d.tangents = hs.p.tangents.empty() ? nullptr : hs.p.tangents.data();
     hs.d.light_extra = hs.p.light_extra.data();
