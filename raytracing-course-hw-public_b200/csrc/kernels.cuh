@@ -118,9 +118,6 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
 #ifndef RT_EXT_SMEM_STACK
 #define RT_EXT_SMEM_STACK 16  // traversal-stack entries per thread kept in shared memory (0: all in local memory)
 #endif
-#ifndef RT_EXT_POP_LOOP
-#define RT_EXT_POP_LOOP 0     // 1: a lane pops until it finds a useful entry (divergent loop)  0: one pop per iteration
-#endif
 #ifndef RT_EXT_MIN_SEARCH
 #define RT_EXT_MIN_SEARCH 16  // leave the inner phase when fewer lanes than this still look for their first leaf
 #endif
@@ -155,7 +152,8 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB) k_extend(
 #else
 __global__ void __launch_bounds__(kExtendThreads) k_extend(
 #endif
-    DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce) {
+    DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce, uint32_t one) {
+    // `one` = 0x3F800000, passed as an argument so that it is not an immediate (see qplane() in pt_core.cuh)
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
     const float4 *__restrict__ qo = q.o[bounce & 1];
@@ -164,16 +162,17 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    // postponed far children: link and entry distance
-    __shared__ int32_t s_link[kSmemStack > 0 ? kSmemStack : 1][kExtendThreads];
-    __shared__ float s_dist[kSmemStack > 0 ? kSmemStack : 1][kExtendThreads];
+    // postponed far children: plane 0 = link, plane 1 = entry distance; `top` walks this thread's column
+    constexpr int kPlane = (kSmemStack > 0 ? kSmemStack : 1) * kExtendThreads;
+    __shared__ uint32_t s_stack[2 * kPlane];
     float2 overflow[RT_STACK_SIZE - kSmemStack];
-    const uint32_t tid = threadIdx.x;
+    uint32_t *top = s_stack + threadIdx.x;  // slot of the NEXT push (valid while sp < kSmemStack)
     int sp = 0;
     int32_t link = kLinkDone;  // >= 0 inner node, kLinkPop / kLinkDone, otherwise a leaf (~first triangle)
     int32_t leaf = 0;          // postponed leaf link (always < 0) or 0 = none
     uint32_t ray = kNoRay;
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1), ood = mk3(0, 0, 0);
+    RaySwz sw = ray_swizzle(idir);
     float best_t = INFINITY, best_b = 0.0f, best_c = 0.0f;
     int32_t best_tri = -1;
     // A pending ray (bit 31 of its sample index) is traversed twice: first through the light BVH, all hits, summing
@@ -228,10 +227,12 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 d = mk3(d4.x, d4.y, d4.z);
                 idir = mk3(rcp_rn(d.x), rcp_rn(d.y), rcp_rn(d.z));
                 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+                sw = ray_swizzle(idir);
                 best_t = INFINITY;
                 best_b = best_c = 0.0f;
                 best_tri = -1;
                 sp = 0;
+                top = s_stack + threadIdx.x;
                 lmode = (__float_as_uint(d4.w) >> 31) != 0u && lbvh.root != RT_LINK_NONE;
                 lsum = 0.0f;
                 if (lmode) {
@@ -254,73 +255,59 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
         for (;;) {
             // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
             //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)
-#if RT_EXT_POP_LOOP
-            while (link == kLinkPop) {
-#else
-            if (link == kLinkPop) {
-#endif
-                if (sp == 0) {
-                    link = kLinkDone;
-                } else {
+            {
+                const bool need = link == kLinkPop;
+                const bool has = need && sp > 0;
+                int32_t l = kLinkDone;
+                float t = -INFINITY;  // empty stack: t < best_t holds, link becomes kLinkDone
+                if (has) {
                     --sp;
-                    int32_t l;
-                    float t;
                     if (kSmemStack > 0 && sp < kSmemStack) {
-                        l = s_link[sp][tid];
-                        t = s_dist[sp][tid];
+                        top -= kExtendThreads;
+                        l = static_cast<int32_t>(top[0]);
+                        t = __uint_as_float(top[kPlane]);
                     } else {
                         const float2 e = overflow[sp - kSmemStack];
                         l = __float_as_int(e.x);
                         t = e.y;
                     }
-                    link = t < best_t ? l : kLinkPop;
                 }
-            }
-            // (1b) a pending ray whose light-BVH traversal is complete starts its scene traversal at once
-            if (lmode && link == kLinkDone && leaf == 0) {
-                q.lpdf[ray] = lsum * inv_n_lights;
-                lmode = false;
-                node_base = bvh.qnodes;
-                tri_base = bvh.tris;
-                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
+                if (need) link = t < best_t ? l : kLinkPop;
             }
             // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
             if (leaf == 0 && link_is_leaf(link)) {
                 leaf = link;
                 link = kLinkPop;
             }
-            // (3) phase vote
-            const bool searching = leaf == 0 && link != kLinkDone;
-            const uint32_t m_search = __ballot_sync(FULL, searching);
-            if (m_search == 0) break;
-            if (kMinSearching > 1 && __popc(m_search) < kMinSearching) {
+            // (3) phase vote: go on while at least kMinSearching lanes still look for their first leaf
+            const uint32_t m_search = __ballot_sync(FULL, leaf == 0 && link != kLinkDone);
+            if (__popc(m_search) < kMinSearching) {
+                if (m_search == 0) break;
                 // few lanes still search: go and do useful work for the others if there is any (pending
                 // leaves to intersect, or finished lanes that can take a new ray); else keep going
-                const bool other_work = leaf != 0 || (can_refill && link == kLinkDone);
-                if (__any_sync(FULL, other_work)) break;
+                if (__any_sync(FULL, leaf != 0 || (can_refill && link == kLinkDone))) break;
             }
             // (4) at most one node step
             if (link >= 0) {
                 const f8 nq = ld8(node_base + link);  // 32 B quantised node = one sector, one 256-bit load
-                const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood,
-                                               eps, best_t);
-                const bool hl = nt.hl, hr = nt.hr;
-                const float dl = nt.dl, dr = nt.dr;
+                const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
+                                               one, eps, best_t);
                 const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
                 // near child first; ties go left (bvh.h:216-219)
-                const bool right_first = hr && (!hl || dl > dr);
-                if (hl && hr) {
+                const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);
+                if (nt.hl && nt.hr) {
                     const int32_t far_link = right_first ? ll : lr;
-                    const float far_t = right_first ? dl : dr;
+                    const float far_t = right_first ? nt.dl : nt.dr;
                     if (kSmemStack > 0 && sp < kSmemStack) {
-                        s_link[sp][tid] = far_link;
-                        s_dist[sp][tid] = far_t;
+                        top[0] = static_cast<uint32_t>(far_link);
+                        top[kPlane] = __float_as_uint(far_t);
+                        top += kExtendThreads;
                     } else {
                         overflow[sp - kSmemStack] = make_float2(__int_as_float(far_link), far_t);
                     }
                     ++sp;
                 }
-                link = (hl || hr) ? (right_first ? lr : ll) : kLinkPop;
+                link = (nt.hl || nt.hr) ? (right_first ? lr : ll) : kLinkPop;
             }
         }
 

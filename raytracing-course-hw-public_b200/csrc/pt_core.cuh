@@ -193,36 +193,58 @@ RT_HD bool tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float min_dst, float &t, flo
 //   t(q) = (org + q * cell - o) / d = fma(1 + q * 2^-15, A, B)   with  A = 2^15 * cell / d,  B = (org - o) / d - A
 // costs one PRMT + one FFMA per plane and no integer->float conversion.  A is 128 x the node's extent in ray
 // space, so B carries an absolute rounding error of ~2^-9 cell; the packer keeps a 1/64-cell margin for it.
-template <int K> RT_HD float qplane(uint32_t w) {
+// `one` = 0x3F800000, which k_extend receives as a kernel ARGUMENT: PRMT takes one immediate, and it has to be the
+// selector — when the compiler sees the constant it makes that the immediate and re-materialises all the selectors
+// in registers (14 extra moves per node step).
+template <int K> RT_HD float qplane(uint32_t w, uint32_t one) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (K << 4)));
+    return __uint_as_float(__byte_perm(w, one, 0x7604u | (K << 4)));
 #else
-    return u2f(0x3F800000u | (((w >> (8 * K)) & 255u) << 8));
+    return u2f(one | (((w >> (8 * K)) & 255u) << 8));
 #endif
 }
+RT_HD uint32_t qnode_one() { return 0x3F800000u; }  // the kernel gets it as an argument instead
 
 struct NodeTest {
     float dl, dr;  // entry distances (clipped to eps from below)
     bool hl, hr;
 };
 
+// Per-ray byte selectors: identity where the ray runs in the positive direction of the axis, min<->max swapped
+// where it runs in the negative one; applied to a plane word they give (left.near, left.far, right.near, right.far).
+struct RaySwz {
+    uint32_t x, y, z;
+};
+RT_HD RaySwz ray_swizzle(f3 idir) {
+    RaySwz r;
+    r.x = idir.x < 0.0f ? 0x2301u : 0x3210u;
+    r.y = idir.y < 0.0f ? 0x2301u : 0x3210u;
+    r.z = idir.z < 0.0f ? 0x2301u : 0x3210u;
+    return r;
+}
+RT_HD uint32_t swz(uint32_t w, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, sel);
+#else
+    return sel == 0x3210u ? w : (((w & 0x00FF00FFu) << 8) | ((w >> 8) & 0x00FF00FFu));
+#endif
+}
+
 RT_HD NodeTest qnode_test(const uint32_t ox, const uint32_t oy, const uint32_t oz, const uint32_t q0, const uint32_t q1,
-                          const uint32_t q2, f3 idir, f3 ood, float eps, float best_t) {
+                          const uint32_t q2, f3 idir, f3 ood, RaySwz sw, uint32_t one, float eps, float best_t) {
     const float ax = u2f((ox << 23) + 0x07800000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
     const float ay = u2f((oy << 23) + 0x07800000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
     const float az = u2f((oz << 23) + 0x07800000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
-    const float lx0 = fmaf(qplane<0>(q0), ax, bx), ly0 = fmaf(qplane<1>(q0), ay, by), lz0 = fmaf(qplane<2>(q0), az, bz);
-    const float lx1 = fmaf(qplane<3>(q0), ax, bx), ly1 = fmaf(qplane<0>(q1), ay, by), lz1 = fmaf(qplane<1>(q1), az, bz);
-    const float rx0 = fmaf(qplane<2>(q1), ax, bx), ry0 = fmaf(qplane<3>(q1), ay, by), rz0 = fmaf(qplane<0>(q2), az, bz);
-    const float rx1 = fmaf(qplane<1>(q2), ax, bx), ry1 = fmaf(qplane<2>(q2), ay, by), rz1 = fmaf(qplane<3>(q2), az, bz);
-    // slab test of both children (bvh.h:137-152), interval clipped to [eps, best_t] inside the min/max chain
-    // (hit <=> lo <= hi): visits the boxes `t_min <= t_max && t_max >= eps && max(t_min, eps) < best` does,
-    // plus harmless ties with best_t.  fminf/fmaxf drop NaNs (ray parallel to a slab): conservative.
+    const uint32_t wx = swz(q0, sw.x), wy = swz(q1, sw.y), wz = swz(q2, sw.z);
+    // slab test of both children (bvh.h:137-152): entry = max of the three near planes, exit = min of the three far
+    // planes, interval clipped to [eps, best_t] (hit <=> entry <= exit): visits the boxes
+    // `t_min <= t_max && t_max >= eps && max(t_min, eps) < best` does, plus harmless ties with best_t.  A ray parallel
+    // to a slab gives NaN or +-inf planes; fmaxf/fminf drop the NaNs: conservative.
     NodeTest r;
-    r.dl = fmaxf(fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fminf(lz0, lz1)), eps);
-    const float el = fminf(fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1)), best_t);
-    r.dr = fmaxf(fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fminf(rz0, rz1)), eps);
-    const float er = fminf(fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1)), best_t);
+    r.dl = fmaxf(fmaxf(fmaxf(fmaf(qplane<0>(wx, one), ax, bx), fmaf(qplane<0>(wy, one), ay, by)), fmaf(qplane<0>(wz, one), az, bz)), eps);
+    const float el = fminf(fminf(fminf(fmaf(qplane<1>(wx, one), ax, bx), fmaf(qplane<1>(wy, one), ay, by)), fmaf(qplane<1>(wz, one), az, bz)), best_t);
+    r.dr = fmaxf(fmaxf(fmaxf(fmaf(qplane<2>(wx, one), ax, bx), fmaf(qplane<2>(wy, one), ay, by)), fmaf(qplane<2>(wz, one), az, bz)), eps);
+    const float er = fminf(fminf(fminf(fmaf(qplane<3>(wx, one), ax, bx), fmaf(qplane<3>(wy, one), ay, by)), fmaf(qplane<3>(wz, one), az, bz)), best_t);
     r.hl = r.dl <= el;
     r.hr = r.dr <= er;
     return r;
@@ -238,6 +260,7 @@ RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst) {
     if (bvh.root == RT_LINK_NONE) return best;
     const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const RaySwz sw = ray_swizzle(idir);
     int32_t stack_link[RT_STACK_SIZE];
     float stack_t[RT_STACK_SIZE];
     int sp = 0;
@@ -245,8 +268,8 @@ RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst) {
     for (;;) {
         if (link >= 0) {
             const f8 nq = ld8(bvh.qnodes + link);
-            const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood,
-                                           min_dst, best.t);
+            const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
+                                           qnode_one(), min_dst, best.t);
             const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
             if (nt.hl || nt.hr) {
                 const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);

@@ -172,12 +172,10 @@ inline int quantize_nodes(const std::vector<DNode> &nodes, std::vector<QNode> &o
         QNode &o = out[i];
         for (int a = 0; a < 3; ++a)
             if (!quantize_axis(lo[a], hi[a], o.org[a], q[a])) return RT_ERR_BAD_SCENE;
-        // byte order = DNode's plane order: lminx lminy lminz lmaxx | lmaxy lmaxz rminx rminy | rminz rmaxx rmaxy rmaxz
-        const uint8_t b[12] = {q[0][0], q[1][0], q[2][0], q[0][1], q[1][1], q[2][1],
-                               q[0][2], q[1][2], q[2][2], q[0][3], q[1][3], q[2][3]};
+        // one word per axis: left.min, left.max, right.min, right.max (quantize_axis's order)
         for (int w = 0; w < 3; ++w)
-            o.q[w] = static_cast<uint32_t>(b[4 * w]) | static_cast<uint32_t>(b[4 * w + 1]) << 8 |
-                     static_cast<uint32_t>(b[4 * w + 2]) << 16 | static_cast<uint32_t>(b[4 * w + 3]) << 24;
+            o.q[w] = static_cast<uint32_t>(q[w][0]) | static_cast<uint32_t>(q[w][1]) << 8 |
+                     static_cast<uint32_t>(q[w][2]) << 16 | static_cast<uint32_t>(q[w][3]) << 24;
         o.left = n.left;
         o.right = n.right;
     }

@@ -295,19 +295,20 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     // their rays while the other SMs idle, so throughput grows with the batch: 8 Mi / 16 / 32 / 64 / 128 /
     // 256 Mi paths -> 771 / 819 / 845 / 881 / 896 / 910 Msamples/s on config 4 (B200, measured).  The default
     // is 128 Mi paths (416 B of queue state each = 53 GB of the 180 GB), capped at half of the free memory.
+    const size_t want_total = n_pix * static_cast<size_t>(s_end - s_begin);
     size_t max_paths = rp.max_paths_in_flight;
     if (max_paths == 0) {
         max_paths = static_cast<size_t>(128) << 20;
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            size_t held = 0;  // what this handle already holds for queues counts as available
-            for (int i = 0; i < 2; ++i) held += (d.qo[i].n + d.qd[i].n + d.qthr[i].n) * sizeof(float4);
-            held += (d.hit.n + d.rad.n) * sizeof(float4);
-            max_paths = std::min(max_paths, (free_b + held) / 2 / kBytesPerPath);
+        // the memory query is a slow, jittery driver call (tens of ms with 50 GB allocated): only when the queues
+        // would have to grow beyond what this handle already holds
+        if (std::min(max_paths, want_total) > d.hit.n) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                max_paths = std::min(max_paths, std::max(d.hit.n, (free_b + d.hit.n * kBytesPerPath) / 2 / kBytesPerPath));
         }
     }
     max_paths = std::max<size_t>(max_paths, 1024);
-    const size_t cap = std::min(max_paths, n_pix * static_cast<size_t>(s_end - s_begin));
+    const size_t cap = std::min(max_paths, want_total);
     for (int i = 0; i < 2; ++i) {
         if (int rc = d.qo[i].alloc(cap)) return rc;
         if (int rc = d.qd[i].alloc(cap)) return rc;
@@ -357,7 +358,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
             rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q);
             mark(ctx, d, K_GENERATE);
             if (ids_mode) {  // pixel-centre rays through the same traversal kernel, then hit -> scene.objects id
-                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, 0);
+                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, 0, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
                 rt::k_ids_from_hits<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.hit.p, d.scene.scene.tris, d.prim_ids.p);
                 mark(ctx, d, K_IDS);
@@ -365,7 +366,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
                 continue;
             }
             for (uint32_t b = 0; b < depth; ++b) {
-                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b);
+                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
                 rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b);
                 mark(ctx, d, K_SHADE);

@@ -42,8 +42,10 @@ struct alignas(64) DNode {
 //                cell exponent, is part of the origin's mantissa; the packer rounds such that this
 //                value is <= the exact minimum); bit 8 is always 0.
 //   cell[axis] = 2^(e - 127), e = org[axis] & 0xFF (a float exponent field).
-//   q[0] bytes: l.minx l.miny l.minz l.maxx   q[1]: l.maxy l.maxz r.minx r.miny   q[2]: r.minz r.maxx r.maxy r.maxz
-//   (the plane order of DNode).
+//   q[axis] bytes (low to high): left.min, left.max, right.min, right.max along that axis — one word per
+//   axis, so that ONE byte permute with a per-ray selector (swap min/max where the ray runs in the negative
+//   direction) turns it into (left.near, left.far, right.near, right.far) and the slab test needs no pairwise
+//   min/max.
 struct alignas(32) QNode {
     uint32_t org[3];
     uint32_t q[3];

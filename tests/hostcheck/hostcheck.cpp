@@ -157,13 +157,14 @@ int hc_qnode_check(const rt_scene_desc *sc, double *out) {
         const float exact[12] = {n.lminx, n.lminy, n.lminz, n.lmaxx, n.lmaxy, n.lmaxz,
                                  n.rminx, n.rminy, n.rminz, n.rmaxx, n.rmaxy, n.rmaxz};
         double dec[12];
-        for (int k = 0; k < 12; ++k) {
+        for (int k = 0; k < 12; ++k) {  // k = DNode plane order: child (k / 6), min/max ((k / 3) & 1), axis (k % 3)
             const int axis = k % 3;
             const bool is_max = (k / 3) & 1;
+            const int child = k / 6;
             const uint32_t word = q.org[axis];
             if (word & 0x100u) return -102;
             const double org = (double)u2f(word), cell = ldexp(1.0, (int)(word & 255u) - 127);
-            const uint32_t byte = (q.q[k / 4] >> (8 * (k % 4))) & 255u;
+            const uint32_t byte = (q.q[axis] >> (8 * (2 * child + (is_max ? 1 : 0)))) & 255u;
             dec[k] = org + byte * cell;
             const double slack = is_max ? dec[k] - (double)exact[k] : (double)exact[k] - dec[k];
             if (slack < 0) ++bad;
