@@ -16,6 +16,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "ncu launches rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 1 -c 3 -f -o gpurun_out/${TAG}_extend $CMD > gpurun_out/${TAG}_ncu_extend.log 2>&1
 echo "ncu extend rc=$?"
+# DRAM bytes of ALL k_extend launches of one step (16 spp = one batch = 8 launches) -> bytes per extension ray
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_extend -c 8 --csv \
+    --log-file gpurun_out/${TAG}_extend_dram.csv $CMD > gpurun_out/${TAG}_ncu_extend_dram.log 2>&1
+echo "ncu extend dram rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 1 -c 2 -f -o gpurun_out/${TAG}_shade $CMD > gpurun_out/${TAG}_ncu_shade.log 2>&1
 echo "ncu shade rc=$?"
 exit 0
