@@ -131,6 +131,10 @@ constexpr uint32_t kRayBlock = 128;
 // per launch, 31 % of the kernel's L1 sectors — profiles/r1_v2_k_extend_ncu_full.csv).
 constexpr int kSmemStack = RT_EXT_SMEM_STACK;
 constexpr int kMinSearching = RT_EXT_MIN_SEARCH;
+#ifndef RT_EXT_STEPS_PER_VOTE
+#define RT_EXT_STEPS_PER_VOTE 3  // 1 / 2 / 3 / 4 -> 103.4 / 100.4 / 99.3 / 100.4 ms of k_extend per 128 spp
+#endif
+constexpr int kStepsPerVote = RT_EXT_STEPS_PER_VOTE;
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
 // MUFU.RCP (1 ulp): one instruction instead of the IEEE division's Newton step + slow path
@@ -253,33 +257,8 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
 
         // ---- inner phase -------------------------------------------------------------------------------
         for (;;) {
-            // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
-            //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)
-            {
-                const bool need = link == kLinkPop;
-                const bool has = need && sp > 0;
-                int32_t l = kLinkDone;
-                float t = -INFINITY;  // empty stack: t < best_t holds, link becomes kLinkDone
-                if (has) {
-                    --sp;
-                    if (kSmemStack > 0 && sp < kSmemStack) {
-                        top -= kExtendThreads;
-                        l = static_cast<int32_t>(top[0]);
-                        t = __uint_as_float(top[kPlane]);
-                    } else {
-                        const float2 e = overflow[sp - kSmemStack];
-                        l = __float_as_int(e.x);
-                        t = e.y;
-                    }
-                }
-                if (need) link = t < best_t ? l : kLinkPop;
-            }
-            // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
-            if (leaf == 0 && link_is_leaf(link)) {
-                leaf = link;
-                link = kLinkPop;
-            }
-            // (3) phase vote: go on while at least kMinSearching lanes still look for their first leaf
+            // (3) phase vote, once per kStepsPerVote node steps: go on while at least kMinSearching lanes still look
+            //     for their first leaf (a lane that has nothing to do in a step simply idles through it)
             const uint32_t m_search = __ballot_sync(FULL, leaf == 0 && link != kLinkDone);
             if (__popc(m_search) < kMinSearching) {
                 if (m_search == 0) break;
@@ -287,27 +266,56 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 // leaves to intersect, or finished lanes that can take a new ray); else keep going
                 if (__any_sync(FULL, leaf != 0 || (can_refill && link == kLinkDone))) break;
             }
-            // (4) at most one node step
-            if (link >= 0) {
-                const f8 nq = ld8(node_base + link);  // 32 B quantised node = one sector, one 256-bit load
-                const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
-                                               one, eps, best_t);
-                const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
-                // near child first; ties go left (bvh.h:216-219)
-                const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);
-                if (nt.hl && nt.hr) {
-                    const int32_t far_link = right_first ? ll : lr;
-                    const float far_t = right_first ? nt.dl : nt.dr;
-                    if (kSmemStack > 0 && sp < kSmemStack) {
-                        top[0] = static_cast<uint32_t>(far_link);
-                        top[kPlane] = __float_as_uint(far_t);
-                        top += kExtendThreads;
-                    } else {
-                        overflow[sp - kSmemStack] = make_float2(__int_as_float(far_link), far_t);
+#pragma unroll
+            for (int step = 0; step < kStepsPerVote; ++step) {
+                // (4) at most one node step
+                if (link >= 0) {
+                    const f8 nq = ld8(node_base + link);  // 32 B quantised node = one sector, one 256-bit load
+                    const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
+                                                   one, eps, best_t);
+                    const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
+                    // near child first; ties go left (bvh.h:216-219)
+                    const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);
+                    if (nt.hl && nt.hr) {
+                        const int32_t far_link = right_first ? ll : lr;
+                        const float far_t = right_first ? nt.dl : nt.dr;
+                        if (kSmemStack > 0 && sp < kSmemStack) {
+                            top[0] = static_cast<uint32_t>(far_link);
+                            top[kPlane] = __float_as_uint(far_t);
+                            top += kExtendThreads;
+                        } else {
+                            overflow[sp - kSmemStack] = make_float2(__int_as_float(far_link), far_t);
+                        }
+                        ++sp;
                     }
-                    ++sp;
+                    link = (nt.hl || nt.hr) ? (right_first ? lr : ll) : kLinkPop;
                 }
-                link = (nt.hl || nt.hr) ? (right_first ? lr : ll) : kLinkPop;
+                // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
+                //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)
+                {
+                    const bool need = link == kLinkPop;
+                    const bool has = need && sp > 0;
+                    int32_t l = kLinkDone;
+                    float t = -INFINITY;  // empty stack: t < best_t holds, link becomes kLinkDone
+                    if (has) {
+                        --sp;
+                        if (kSmemStack > 0 && sp < kSmemStack) {
+                            top -= kExtendThreads;
+                            l = static_cast<int32_t>(top[0]);
+                            t = __uint_as_float(top[kPlane]);
+                        } else {
+                            const float2 e = overflow[sp - kSmemStack];
+                            l = __float_as_int(e.x);
+                            t = e.y;
+                        }
+                    }
+                    if (need) link = t < best_t ? l : kLinkPop;
+                }
+                // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
+                if (leaf == 0 && link_is_leaf(link)) {
+                    leaf = link;
+                    link = kLinkPop;
+                }
             }
         }
 
