@@ -115,11 +115,14 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
 // Compile-time knobs (A/B-tested on the B200, DESIGN.md "k_extend"; defaults = the fastest measured):
 // (64-byte full-precision nodes were the other candidate: equal within 4 % once the kernel was issue-bound, and
 // slower with the SAH tree; removed.)
+#ifndef RT_EXT_WIDE4
+#define RT_EXT_WIDE4 1         // 1: 4-wide quantised nodes (QNode4, two tree levels per step)  0: 2-wide QNode
+#endif
 #ifndef RT_EXT_SMEM_STACK
 #define RT_EXT_SMEM_STACK 16  // traversal-stack entries per thread kept in shared memory (0: all in local memory)
 #endif
 #ifndef RT_EXT_MIN_SEARCH
-#define RT_EXT_MIN_SEARCH 16  // leave the inner phase when fewer lanes than this still look for their first leaf
+#define RT_EXT_MIN_SEARCH 20  // leave the inner phase when fewer lanes than this still look for their first leaf
 #endif
 constexpr int32_t kLinkDone = static_cast<int32_t>(0x80000000u);  // nothing left to traverse
 constexpr int32_t kLinkPop = static_cast<int32_t>(0x80000001u);   // take the next entry from the stack
@@ -169,7 +172,11 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
     // postponed far children: plane 0 = link, plane 1 = entry distance; `top` walks this thread's column
     constexpr int kPlane = (kSmemStack > 0 ? kSmemStack : 1) * kExtendThreads;
     __shared__ uint32_t s_stack[2 * kPlane];
+#if RT_EXT_WIDE4
+    float2 overflow[96 - kSmemStack];  // up to three pushes per level of a tree half as deep as the binary one
+#else
     float2 overflow[RT_STACK_SIZE - kSmemStack];
+#endif
     uint32_t *top = s_stack + threadIdx.x;  // slot of the NEXT push (valid while sp < kSmemStack)
     int sp = 0;
     int32_t link = kLinkDone;  // >= 0 inner node, kLinkPop / kLinkDone, otherwise a leaf (~first triangle)
@@ -185,7 +192,16 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
     // this kernel's lane occupancy and refill instead of k_shade's (7 of 32 lanes, 57 % of its instructions).
     bool lmode = false;
     float lsum = 0.0f;
-    const QNode *node_base = bvh.qnodes;
+#if RT_EXT_WIDE4
+    typedef QNode4 NodeT;
+#define RT_NODES(b) (b).qnodes4
+#define RT_ROOT(b) (b).root4
+#else
+    typedef QNode NodeT;
+#define RT_NODES(b) (b).qnodes
+#define RT_ROOT(b) (b).root
+#endif
+    const NodeT *node_base = RT_NODES(bvh);
     const DTri *tri_base = bvh.tris;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
@@ -197,9 +213,9 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             if (lmode) {  // light pdf done: now the closest hit of the same ray
                 q.lpdf[ray] = lsum * inv_n_lights;
                 lmode = false;
-                node_base = bvh.qnodes;
+                node_base = RT_NODES(bvh);
                 tri_base = bvh.tris;
-                link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;
+                link = RT_ROOT(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT(bvh);
                 idle = link == kLinkDone;
             }
             if (idle) {
@@ -237,17 +253,17 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 best_tri = -1;
                 sp = 0;
                 top = s_stack + threadIdx.x;
-                lmode = (__float_as_uint(d4.w) >> 31) != 0u && lbvh.root != RT_LINK_NONE;
+                lmode = (__float_as_uint(d4.w) >> 31) != 0u && RT_ROOT(lbvh) != RT_LINK_NONE;
                 lsum = 0.0f;
                 if (lmode) {
-                    node_base = lbvh.qnodes;
+                    node_base = RT_NODES(lbvh);
                     tri_base = lbvh.tris;
-                    link = lbvh.root;
+                    link = RT_ROOT(lbvh);
                 } else {
                     if (__float_as_uint(d4.w) >> 31) q.lpdf[ray] = 0.0f;  // pending, but the scene has no light BVH
-                    node_base = bvh.qnodes;
+                    node_base = RT_NODES(bvh);
                     tri_base = bvh.tris;
-                    link = bvh.root == RT_LINK_NONE ? kLinkDone : bvh.root;  // a leaf root is postponed below
+                    link = RT_ROOT(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT(bvh);  // a leaf root is postponed below
                 }
             }
             pool_next += take;
@@ -270,25 +286,66 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             for (int step = 0; step < kStepsPerVote; ++step) {
                 // (4) at most one node step
                 if (link >= 0) {
+                    auto push = [&](int32_t l, float t) {
+                        if (kSmemStack > 0 && sp < kSmemStack) {
+                            top[0] = static_cast<uint32_t>(l);
+                            top[kPlane] = __float_as_uint(t);
+                            top += kExtendThreads;
+                        } else {
+                            overflow[sp - kSmemStack] = make_float2(__int_as_float(l), t);
+                        }
+                        ++sp;
+                    };
+#if RT_EXT_WIDE4
+                    const char *np = reinterpret_cast<const char *>(node_base + link);
+                    const f8 na = ld8(np), nb = ld8(np + 32);  // 64 B node: grid, 6 plane words, 4 links
+                    const Node4Test nt = qnode4_test(f2u(na.a), f2u(na.b), f2u(na.c), f2u(na.d), f2u(na.e), f2u(na.f), f2u(na.g),
+                                                     f2u(na.h), f2u(nb.a), idir, ood, one, eps, best_t);
+                    float d0 = nt.d[0], d1 = nt.d[1], d2 = nt.d[2], d3 = nt.d[3];
+                    int32_t l0 = static_cast<int32_t>(f2u(nb.b)), l1 = static_cast<int32_t>(f2u(nb.c));
+                    int32_t l2 = static_cast<int32_t>(f2u(nb.d)), l3 = static_cast<int32_t>(f2u(nb.e));
+                    // nearest child first, the others onto the stack farthest first (5-comparator network; ties keep
+                    // the child order, the 4-wide image of "ties go left", bvh.h:216-219)
+                    cswap(d0, l0, d1, l1);
+                    cswap(d2, l2, d3, l3);
+                    cswap(d0, l0, d2, l2);
+                    cswap(d1, l1, d3, l3);
+                    cswap(d1, l1, d2, l2);
+                    // after the sort the hit children are d0..d(n-1); d1..d(n-1) go onto the stack so that d1 is
+                    // on top: three predicated stores below the new top instead of three push sequences
+                    const int n_push = (d1 < INFINITY ? 1 : 0) + (d2 < INFINITY ? 1 : 0) + (d3 < INFINITY ? 1 : 0);
+                    if (kSmemStack > 0 && sp + n_push <= kSmemStack) {
+                        uint32_t *nt_top = top + n_push * kExtendThreads;
+                        if (d1 < INFINITY) {
+                            nt_top[-1 * kExtendThreads] = static_cast<uint32_t>(l1);
+                            nt_top[-1 * kExtendThreads + kPlane] = __float_as_uint(d1);
+                        }
+                        if (d2 < INFINITY) {
+                            nt_top[-2 * kExtendThreads] = static_cast<uint32_t>(l2);
+                            nt_top[-2 * kExtendThreads + kPlane] = __float_as_uint(d2);
+                        }
+                        if (d3 < INFINITY) {
+                            nt_top[-3 * kExtendThreads] = static_cast<uint32_t>(l3);
+                            nt_top[-3 * kExtendThreads + kPlane] = __float_as_uint(d3);
+                        }
+                        top = nt_top;
+                        sp += n_push;
+                    } else {  // rare: the shared part of the stack is full
+                        if (d3 < INFINITY) push(l3, d3);
+                        if (d2 < INFINITY) push(l2, d2);
+                        if (d1 < INFINITY) push(l1, d1);
+                    }
+                    link = d0 < INFINITY ? l0 : kLinkPop;
+#else
                     const f8 nq = ld8(node_base + link);  // 32 B quantised node = one sector, one 256-bit load
                     const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
                                                    one, eps, best_t);
                     const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
                     // near child first; ties go left (bvh.h:216-219)
                     const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);
-                    if (nt.hl && nt.hr) {
-                        const int32_t far_link = right_first ? ll : lr;
-                        const float far_t = right_first ? nt.dl : nt.dr;
-                        if (kSmemStack > 0 && sp < kSmemStack) {
-                            top[0] = static_cast<uint32_t>(far_link);
-                            top[kPlane] = __float_as_uint(far_t);
-                            top += kExtendThreads;
-                        } else {
-                            overflow[sp - kSmemStack] = make_float2(__int_as_float(far_link), far_t);
-                        }
-                        ++sp;
-                    }
+                    if (nt.hl && nt.hr) push(right_first ? ll : lr, right_first ? nt.dl : nt.dr);
                     link = (nt.hl || nt.hr) ? (right_first ? lr : ll) : kLinkPop;
+#endif
                 }
                 // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
                 //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)

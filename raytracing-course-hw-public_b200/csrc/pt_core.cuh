@@ -252,7 +252,7 @@ RT_HD NodeTest qnode_test(const uint32_t ox, const uint32_t oy, const uint32_t o
 
 // closest_hit() over the quantised nodes, in the kernel's arithmetic (1/d once, fused o/d) — the sequential
 // statement of what k_extend computes per ray; the host tests compare its hits with closest_hit()'s.
-RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst) {
+RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst, uint32_t *steps = nullptr) {
     Hit best;
     best.t = INFINITY;
     best.b = best.c = 0.0f;
@@ -267,6 +267,7 @@ RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst) {
     int32_t link = bvh.root;
     for (;;) {
         if (link >= 0) {
+            if (steps) ++*steps;
             const f8 nq = ld8(bvh.qnodes + link);
             const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
                                            qnode_one(), min_dst, best.t);
@@ -279,6 +280,110 @@ RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst) {
                     stack_t[sp] = right_first ? nt.dl : nt.dr;
                     ++sp;
                 }
+                continue;
+            }
+        } else {
+            uint32_t k = static_cast<uint32_t>(~link);
+            for (;;) {
+                const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+                const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+                float t, b, c;
+                if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, min_dst, t, b,
+                             c) &&
+                    t < best.t) {
+                    best.t = t;
+                    best.b = b;
+                    best.c = c;
+                    best.tri = static_cast<int32_t>(k);
+                }
+                if (f2u(t0.w) & RT_LAST_BIT) break;
+                ++k;
+            }
+        }
+        for (;;) {
+            if (sp == 0) return best;
+            --sp;
+            if (stack_t[sp] < best.t) {
+                link = stack_link[sp];
+                break;
+            }
+        }
+    }
+}
+
+// ---- 4-wide quantised node (QNode4): four slab tests from one 64-byte record ------------------------------------
+// near/far plane words are picked per axis by the sign of the ray direction (a register select, no byte permute);
+// d[c] = entry distance of child c clipped to eps from below, or +inf when the child is missed.
+struct Node4Test {
+    float d[4];
+};
+template <int C> RT_HD float q4_entry(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float ax,
+                                      float bx, float ay, float by, float az, float bz, uint32_t one, float eps, float best_t) {
+    const float entry = fmaxf(fmaxf(fmaxf(fmaf(qplane<C>(nx, one), ax, bx), fmaf(qplane<C>(ny, one), ay, by)),
+                                    fmaf(qplane<C>(nz, one), az, bz)), eps);
+    const float exit_ = fminf(fminf(fminf(fmaf(qplane<C>(fx, one), ax, bx), fmaf(qplane<C>(fy, one), ay, by)),
+                                    fmaf(qplane<C>(fz, one), az, bz)), best_t);
+    return entry <= exit_ ? entry : INFINITY;
+}
+RT_HD Node4Test qnode4_test(const uint32_t ox, const uint32_t oy, const uint32_t oz, const uint32_t lox, const uint32_t loy,
+                            const uint32_t loz, const uint32_t hix, const uint32_t hiy, const uint32_t hiz, f3 idir, f3 ood,
+                            uint32_t one, float eps, float best_t) {
+    const float ax = u2f((ox << 23) + 0x07800000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
+    const float ay = u2f((oy << 23) + 0x07800000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
+    const float az = u2f((oz << 23) + 0x07800000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
+    const bool px = !(idir.x < 0.0f), py = !(idir.y < 0.0f), pz = !(idir.z < 0.0f);
+    const uint32_t nx = px ? lox : hix, fx = px ? hix : lox;
+    const uint32_t ny = py ? loy : hiy, fy = py ? hiy : loy;
+    const uint32_t nz = pz ? loz : hiz, fz = pz ? hiz : loz;
+    Node4Test r;
+    r.d[0] = q4_entry<0>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
+    r.d[1] = q4_entry<1>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
+    r.d[2] = q4_entry<2>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
+    r.d[3] = q4_entry<3>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
+    return r;
+}
+// compare-exchange of (distance, link) pairs, ascending by distance; equal distances keep their order (ties: lower
+// child index first, the 4-wide image of "ties go left", bvh.h:216-219)
+RT_HD void cswap(float &da, int32_t &la, float &db, int32_t &lb) {
+    const bool sw = db < da;
+    const float td = sw ? db : da, ud = sw ? da : db;
+    const int32_t tl = sw ? lb : la, ul = sw ? la : lb;
+    da = td; db = ud; la = tl; lb = ul;
+}
+
+// closest_hit() over the 4-wide nodes (sequential statement of k_extend's 4-wide mode); `steps` counts node steps.
+RT_HD Hit closest_hit_q4(const DBvh &bvh, f3 o, f3 d, float min_dst, uint32_t *steps) {
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0.0f;
+    best.tri = -1;
+    if (bvh.root4 == RT_LINK_NONE) return best;
+    const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    int32_t stack_link[RT_STACK_SIZE * 2];
+    float stack_t[RT_STACK_SIZE * 2];
+    int sp = 0;
+    int32_t link = bvh.root4;
+    for (;;) {
+        if (link >= 0) {
+            if (steps) ++*steps;
+            const char *p = reinterpret_cast<const char *>(bvh.qnodes4 + link);
+            const f8 na = ld8(p), nb = ld8(p + 32);
+            const Node4Test nt = qnode4_test(f2u(na.a), f2u(na.b), f2u(na.c), f2u(na.d), f2u(na.e), f2u(na.f), f2u(na.g),
+                                             f2u(na.h), f2u(nb.a), idir, ood, qnode_one(), min_dst, best.t);
+            float d0 = nt.d[0], d1 = nt.d[1], d2 = nt.d[2], d3 = nt.d[3];
+            int32_t l0 = static_cast<int32_t>(f2u(nb.b)), l1 = static_cast<int32_t>(f2u(nb.c));
+            int32_t l2 = static_cast<int32_t>(f2u(nb.d)), l3 = static_cast<int32_t>(f2u(nb.e));
+            cswap(d0, l0, d1, l1);
+            cswap(d2, l2, d3, l3);
+            cswap(d0, l0, d2, l2);
+            cswap(d1, l1, d3, l3);
+            cswap(d1, l1, d2, l2);
+            if (d3 < INFINITY) { stack_link[sp] = l3; stack_t[sp++] = d3; }
+            if (d2 < INFINITY) { stack_link[sp] = l2; stack_t[sp++] = d2; }
+            if (d1 < INFINITY) { stack_link[sp] = l1; stack_t[sp++] = d1; }
+            if (d0 < INFINITY) {
+                link = l0;
                 continue;
             }
         } else {

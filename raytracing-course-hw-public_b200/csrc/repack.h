@@ -19,6 +19,8 @@ namespace rt {
 struct PackedBvh {
     std::vector<DNode> nodes;
     std::vector<QNode> qnodes;    // quantised copy of `nodes` (same indices), see quantize_nodes()
+    std::vector<QNode4> qnodes4;  // 4-wide collapse of the same tree (own indices), see collapse4()
+    int32_t root4 = RT_LINK_NONE;
     std::vector<DTri> tris;       // BVH object order
     std::vector<uint32_t> order;  // BVH position -> scene.objects index
     int32_t root = RT_LINK_NONE;
@@ -118,9 +120,12 @@ inline float bitsf(uint32_t u) {
 // (left lo, left hi, right lo, right hi).  Conservative in exact arithmetic with a margin of 1/64 cell
 // for the device's ray-space rounding (pt_core.cuh, qnode_axis()).  Returns false when the extent
 // cannot be represented (non-finite box).
-inline bool quantize_axis(const float lo[2], const float hi[2], uint32_t &word, uint8_t q[4]) {
-    const float mn = lo[0] < lo[1] ? lo[0] : lo[1];
-    const float mx = hi[0] > hi[1] ? hi[0] : hi[1];
+inline bool quantize_axis_n(const float *lo, const float *hi, int n, uint32_t &word, uint8_t *qlo, uint8_t *qhi) {
+    float mn = lo[0], mx = hi[0];
+    for (int c = 1; c < n; ++c) {
+        mn = lo[c] < mn ? lo[c] : mn;
+        mx = hi[c] > mx ? hi[c] : mx;
+    }
     if (!(std::isfinite(mn) && std::isfinite(mx)) || mx < mn) return false;
     const double margin = 1.0 / 64.0;
     const double ext = static_cast<double>(mx) - static_cast<double>(mn);
@@ -149,17 +154,23 @@ inline bool quantize_axis(const float lo[2], const float hi[2], uint32_t &word, 
         const double top = (static_cast<double>(mx) - org) / cell + margin;
         if (top > 255.0) continue;
         word = w;
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < n; ++c) {
             double a = std::floor((static_cast<double>(lo[c]) - org) / cell - margin);
             double z = std::ceil((static_cast<double>(hi[c]) - org) / cell + margin);
             if (a < 0.0) a = 0.0;  // cannot happen: org <= mn - margin * cell
             if (z > 255.0) z = 255.0;
-            q[2 * c] = static_cast<uint8_t>(a);
-            q[2 * c + 1] = static_cast<uint8_t>(z);
+            qlo[c] = static_cast<uint8_t>(a);
+            qhi[c] = static_cast<uint8_t>(z);
         }
         return true;
     }
     return false;
+}
+inline bool quantize_axis(const float lo[2], const float hi[2], uint32_t &word, uint8_t q[4]) {
+    uint8_t ql[2], qh[2];
+    if (!quantize_axis_n(lo, hi, 2, word, ql, qh)) return false;
+    q[0] = ql[0]; q[1] = qh[0]; q[2] = ql[1]; q[3] = qh[1];
+    return true;
 }
 
 inline int quantize_nodes(const std::vector<DNode> &nodes, std::vector<QNode> &out) {
@@ -180,6 +191,62 @@ inline int quantize_nodes(const std::vector<DNode> &nodes, std::vector<QNode> &o
         o.right = n.right;
     }
     return RT_OK;
+}
+
+// ---- 4-wide collapse ------------------------------------------------------------------------------------------
+struct Child4 {
+    int32_t link;
+    float lo[3], hi[3];
+};
+inline float box_area(const Child4 &c) {
+    const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+inline void children_of(const DNode &n, Child4 out[2]) {
+    out[0] = Child4{n.left, {n.lminx, n.lminy, n.lminz}, {n.lmaxx, n.lmaxy, n.lmaxz}};
+    out[1] = Child4{n.right, {n.rminx, n.rminy, n.rminz}, {n.rmaxx, n.rmaxy, n.rmaxz}};
+}
+// Returns the 4-wide link of binary link `link` (leaves keep their ~first_triangle link).
+inline int32_t collapse4(const std::vector<DNode> &nodes, int32_t link, int32_t null_leaf, std::vector<QNode4> &out, int &rc) {
+    if (link < 0) return link;
+    Child4 ch[4];
+    int n = 2;
+    children_of(nodes[link], ch);
+    while (n < 4) {  // open the inner child with the largest box until four children or only leaves are left
+        int best = -1;
+        float best_area = -1.0f;
+        for (int i = 0; i < n; ++i)
+            if (ch[i].link >= 0 && box_area(ch[i]) > best_area) {
+                best_area = box_area(ch[i]);
+                best = i;
+            }
+        if (best < 0) break;
+        Child4 two[2];
+        children_of(nodes[ch[best].link], two);
+        ch[best] = two[0];
+        ch[n++] = two[1];
+    }
+    const int32_t idx = static_cast<int32_t>(out.size());
+    out.emplace_back();
+    int32_t links[4];
+    for (int i = 0; i < 4; ++i) links[i] = i < n ? collapse4(nodes, ch[i].link, null_leaf, out, rc) : null_leaf;
+    QNode4 &q = out[idx];
+    std::memset(&q, 0, sizeof q);
+    for (int a = 0; a < 3; ++a) {
+        float lo[4], hi[4];
+        uint8_t ql[4] = {255, 255, 255, 255}, qh[4] = {0, 0, 0, 0};  // absent child: inverted box
+        for (int i = 0; i < n; ++i) {
+            lo[i] = ch[i].lo[a];
+            hi[i] = ch[i].hi[a];
+        }
+        if (!quantize_axis_n(lo, hi, n, q.org[a], ql, qh)) rc = RT_ERR_BAD_SCENE;
+        q.lo[a] = static_cast<uint32_t>(ql[0]) | static_cast<uint32_t>(ql[1]) << 8 | static_cast<uint32_t>(ql[2]) << 16 |
+                  static_cast<uint32_t>(ql[3]) << 24;
+        q.hi[a] = static_cast<uint32_t>(qh[0]) | static_cast<uint32_t>(qh[1]) << 8 | static_cast<uint32_t>(qh[2]) << 16 |
+                  static_cast<uint32_t>(qh[3]) << 24;
+    }
+    for (int i = 0; i < 4; ++i) q.link[i] = links[i];
+    return idx;
 }
 
 }  // namespace detail
@@ -205,7 +272,16 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     int rc = RT_OK;
     out.root = detail::pack_node(src, src.root, out, 0, rc);
     if (rc) return rc;
-    return detail::quantize_nodes(out.nodes, out.qnodes);
+    if (int rq = detail::quantize_nodes(out.nodes, out.qnodes)) return rq;
+    // 4-wide collapse; the null leaf (absent children) is one degenerate triangle appended after the real ones
+    out.qnodes4.clear();
+    DTri null_tri;
+    std::memset(&null_tri, 0, sizeof null_tri);
+    null_tri.id_last = RT_LAST_BIT;
+    out.tris.push_back(null_tri);
+    const int32_t null_leaf = ~static_cast<int32_t>(out.tris.size() - 1);
+    out.root4 = detail::collapse4(out.nodes, out.root, null_leaf, out.qnodes4, rc);
+    return rc;
 }
 
 // `rebuild_scene_bvh`: build the scene BVH with the library's SAH builder (sah_build.h) over the triangles of
@@ -305,6 +381,8 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
 inline void fill_scene_constants(const rt_scene_desc &sc, const PackedScene &p, DScene &d) {
     std::memset(&d, 0, sizeof d);
     d.scene.root = p.scene.root;
+    d.scene.root4 = p.scene.root4;
+    d.light.root4 = p.light.root4;
     d.scene.n_tris = static_cast<uint32_t>(p.scene.tris.size());
     d.light.root = p.light.root;
     d.light.n_tris = static_cast<uint32_t>(p.light.tris.size());

@@ -107,6 +107,7 @@ struct DeviceState {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
     // scene
     DevBuf<QNode> qnodes, lqnodes;  // scene BVH and light BVH, quantised (both traversed by k_extend)
+    DevBuf<QNode4> qnodes4, lqnodes4;  // their 4-wide collapses
     DevBuf<DTri> tris, ltris, lsample;
     DevBuf<DAttr> attrs;
     DevBuf<DTangent> tangents;
@@ -161,8 +162,13 @@ namespace {
 
 int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p) {
     CU_CHECK(cudaSetDevice(d.device));
+#if RT_EXT_WIDE4  // only the node format the traversal kernel was built for goes to the device
+    if (int rc = d.qnodes4.upload(p.scene.qnodes4, d.stream)) return rc;
+    if (int rc = d.lqnodes4.upload(p.light.qnodes4, d.stream)) return rc;
+#else
     if (int rc = d.qnodes.upload(p.scene.qnodes, d.stream)) return rc;
     if (int rc = d.lqnodes.upload(p.light.qnodes, d.stream)) return rc;
+#endif
     if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
     if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
     if (int rc = d.lsample.upload(p.light_sample, d.stream)) return rc;
@@ -177,6 +183,8 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     rt::fill_scene_constants(sc, p, d.scene);
     d.scene.scene.nodes = nullptr;  // the device traverses the quantised copies only
     d.scene.scene.qnodes = d.qnodes.p;
+    d.scene.scene.qnodes4 = d.qnodes4.p;
+    d.scene.light.qnodes4 = d.lqnodes4.p;
     d.scene.scene.tris = d.tris.p;
     d.scene.light.nodes = nullptr;
     d.scene.light.qnodes = d.lqnodes.p;
@@ -450,7 +458,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        d.qnodes.release(); d.lqnodes.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
+        d.qnodes.release(); d.lqnodes.release(); d.qnodes4.release(); d.lqnodes4.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }

@@ -52,6 +52,17 @@ struct alignas(32) QNode {
     int32_t left, right;  // links
 };
 
+// 4-wide quantised node (collapse of two levels of the binary tree): same grid as QNode, per axis one word with the
+// four children's min planes and one with their max planes.  Absent children (a wide node has 2..4) carry the
+// link of the "null leaf" (one degenerate triangle at the end of the triangle array) and an inverted box.
+struct alignas(64) QNode4 {
+    uint32_t org[3];
+    uint32_t lo[3];   // per axis: min-plane bytes of children 0..3
+    uint32_t hi[3];   // per axis: max-plane bytes of children 0..3
+    int32_t link[4];
+    uint32_t pad[3];
+};
+
 struct alignas(64) DTri {
     float ax, ay, az;
     uint32_t id_last;  // scene.objects index | RT_LAST_BIT on the last triangle of a leaf
@@ -97,7 +108,9 @@ struct alignas(16) DLight {  // light triangle extras, light-BVH order
 
 struct DBvh {
     const DNode *nodes;    // full-precision nodes (light BVH traversal, host checks); may be null on the device
-    const QNode *qnodes;   // quantised nodes (k_extend); null for the light BVH
+    const QNode *qnodes;   // quantised 2-wide nodes
+    const QNode4 *qnodes4; // quantised 4-wide nodes (collapsed tree) and their root link
+    int32_t root4;
     const DTri *tris;
     int32_t root;  // link; RT_LINK_NONE when empty
     uint32_t n_tris;

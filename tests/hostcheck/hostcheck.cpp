@@ -26,6 +26,8 @@ int build(const rt_scene_desc *sc, HostScene &hs) {
     fill_scene_constants(*sc, hs.p, hs.d);
     hs.d.scene.nodes = hs.p.scene.nodes.data();
     hs.d.scene.qnodes = hs.p.scene.qnodes.data();
+    hs.d.scene.qnodes4 = hs.p.scene.qnodes4.data();
+    hs.d.light.qnodes4 = hs.p.light.qnodes4.data();
     hs.d.light.qnodes = hs.p.light.qnodes.data();
     hs.d.scene.tris = hs.p.scene.tris.data();
     hs.d.light.nodes = hs.p.light.nodes.data();
@@ -137,6 +139,31 @@ int hc_primary_ids_q(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *i
             const Hit hit = closest_hit_q(hs.d.scene, cam.pos, dir, hs.d.eps);
             ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
         }
+    return 0;
+}
+
+// Primary ids through the 4-wide nodes; steps[0] / steps[1] = node steps of the 4-wide / 2-wide traversal summed over
+// all pixels (how many fewer, fatter steps the collapse buys).
+int hc_primary_ids_q4(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids, uint64_t *steps) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    const Camera cam = make_camera(hs.d, w, h);
+    uint64_t s4 = 0, s2 = 0;
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
+            uint32_t st = 0;
+            const Hit hit = closest_hit_q4(hs.d.scene, cam.pos, dir, hs.d.eps, &st);
+            s4 += st;
+            uint32_t st2 = 0;
+            closest_hit_q(hs.d.scene, cam.pos, dir, hs.d.eps, &st2);
+            s2 += st2;
+            ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
+        }
+    if (steps) {
+        steps[0] = s4;
+        steps[1] = s2;
+    }
     return 0;
 }
 
