@@ -152,6 +152,8 @@ typedef struct rt_render_params {
     uint64_t seed;           /* Philox key */
     uint32_t max_paths_in_flight; /* 0 => default (128 Mi paths, at most half of the free device memory) */
     uint32_t flags;          /* RT_FLAG_* */
+    uint32_t pixel_begin;    /* this call renders the row-major pixels [pixel_begin, pixel_end) only (the other */
+    uint32_t pixel_end;      /* pixels' sums stay 0 / untouched); 0 => width * height.  Image-tile split. */
 } rt_render_params;
 
 #define RT_FLAG_ACCUMULATE 1u /* add to the existing sums instead of clearing them */
@@ -220,7 +222,9 @@ typedef struct rt_text_scene {
 typedef struct rt_gpu_ctx rt_gpu_ctx;
 
 /* n_gpus devices starting at first_device (single-process multi-device: one
- * stream per device, ncclReduce to device 0).  Use n_gpus = 1 and the rank's
+ * stream per device, ncclReduce to device 0).  A render splits the SAMPLES of
+ * every pixel over the devices; when there are fewer samples than devices it
+ * splits the IMAGE into contiguous pixel ranges instead (all samples each).  Use n_gpus = 1 and the rank's
  * own device when the caller runs one process per GPU. */
 int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device);
 void rt_gpu_destroy(rt_gpu_ctx *ctx);

@@ -74,7 +74,8 @@ class rt_scene_desc(C.Structure):
 class rt_render_params(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("samples", C.c_uint32), ("sample_begin", C.c_uint32),
                 ("sample_end", C.c_uint32), ("mode", C.c_uint32), ("seed", C.c_uint64),
-                ("max_paths_in_flight", C.c_uint32), ("flags", C.c_uint32)]
+                ("max_paths_in_flight", C.c_uint32), ("flags", C.c_uint32), ("pixel_begin", C.c_uint32),
+                ("pixel_end", C.c_uint32)]
 
 
 class rt_stats(C.Structure):

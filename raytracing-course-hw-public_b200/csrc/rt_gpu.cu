@@ -240,9 +240,12 @@ int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params 
     d.events_used = 0;
     CU_CHECK(cudaEventRecord(d.ev_begin, d.stream));
     mark(ctx, d, -1);
-    const unsigned long long hs[4] = {0, 0, 0, ids_mode ? 0ull : static_cast<unsigned long long>(n_pix) * (s_end - s_begin)};
+    const uint32_t px_begin = ids_mode ? 0u : rp.pixel_begin;
+    const uint32_t px_end = ids_mode || rp.pixel_end == 0 ? static_cast<uint32_t>(n_pix) : rp.pixel_end;
+    const uint32_t n_render = px_end > px_begin ? px_end - px_begin : 0u;
+    const unsigned long long hs[4] = {0, 0, 0, ids_mode ? 0ull : static_cast<unsigned long long>(n_render) * (s_end - s_begin)};
     CU_CHECK(cudaMemcpyAsync(d.stats.p, hs, sizeof hs, cudaMemcpyHostToDevice, d.stream));
-    if (ids_mode || (s_end > s_begin && d.tscene.ray_depth > 0)) {
+    if (n_render > 0 && (ids_mode || (s_end > s_begin && d.tscene.ray_depth > 0))) {
         rt::Camera cam;
         DScene tmp;
         std::memset(&tmp, 0, sizeof tmp);
@@ -262,7 +265,9 @@ int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params 
         tp.k0 = static_cast<uint32_t>(rp.seed);
         tp.k1 = static_cast<uint32_t>(rp.seed >> 32);
         tp.ids = ids_mode ? 1u : 0u;
-        rtt::k_text_render<<<static_cast<unsigned>((n_pix + 127) / 128), 128, 0, d.stream>>>(d.tscene, cam, tp, d.accum.p, d.prim_ids.p);
+        tp.pix0 = px_begin;
+        tp.npix = n_render;
+        rtt::k_text_render<<<(n_render + 127) / 128, 128, 0, d.stream>>>(d.tscene, cam, tp, d.accum.p, d.prim_ids.p);
         mark(ctx, d, K_SHADE);
         launches += 1;
     }
@@ -289,7 +294,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     CU_CHECK(cudaEventRecord(d.ev_begin, d.stream));
     mark(ctx, d, -1);
 
-    if (!ids_mode && (s_end <= s_begin || depth == 0)) {  // run_raytracer returns early for ray_depth == 0, raytracer.h:630
+    if (!ids_mode && (s_end <= s_begin || depth == 0 || (rp.pixel_end != 0 && rp.pixel_end <= rp.pixel_begin))) {  // run_raytracer returns early for ray_depth == 0, raytracer.h:630
         CU_CHECK(cudaEventRecord(d.ev_end, d.stream));
         return RT_OK;
     }
@@ -303,7 +308,9 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     // their rays while the other SMs idle, so throughput grows with the batch: 8 Mi / 16 / 32 / 64 / 128 /
     // 256 Mi paths -> 771 / 819 / 845 / 881 / 896 / 910 Msamples/s on config 4 (B200, measured).  The default
     // is 128 Mi paths (416 B of queue state each = 53 GB of the 180 GB), capped at half of the free memory.
-    const size_t want_total = n_pix * static_cast<size_t>(s_end - s_begin);
+    const size_t px_begin = ids_mode ? 0 : rp.pixel_begin, px_end = ids_mode || rp.pixel_end == 0 ? n_pix : rp.pixel_end;
+    const size_t n_render = px_end - px_begin;  // image-tile split: only this pixel range is rendered
+    const size_t want_total = n_render * static_cast<size_t>(s_end - s_begin);
     size_t max_paths = rp.max_paths_in_flight;
     if (max_paths == 0) {
         max_paths = static_cast<size_t>(128) << 20;
@@ -352,9 +359,9 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     bp.centre = ids_mode ? 1u : 0u;
 
     // batches: all pixels x k samples when the image fits, else pixel chunks x 1 sample
-    const size_t pix_chunk = std::min(n_pix, cap);
-    for (size_t pix0 = 0; pix0 < n_pix; pix0 += pix_chunk) {
-        const uint32_t npix = static_cast<uint32_t>(std::min(pix_chunk, n_pix - pix0));
+    const size_t pix_chunk = std::max<size_t>(1, std::min(n_render, cap));
+    for (size_t pix0 = px_begin; pix0 < px_end; pix0 += pix_chunk) {
+        const uint32_t npix = static_cast<uint32_t>(std::min(pix_chunk, px_end - pix0));
         const uint32_t k_max = static_cast<uint32_t>(std::max<size_t>(1, cap / npix));
         for (uint32_t s0 = s_begin; s0 < s_end; s0 += k_max) {
             bp.pix0 = static_cast<uint32_t>(pix0);
@@ -567,14 +574,28 @@ int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params) {
     if (rp.mode == RT_MODE_BEAUTY && rp.samples == 0) return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: samples == 0");
     if (rp.sample_end == 0) rp.sample_end = rp.samples;
     if (rp.sample_begin > rp.sample_end) return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: sample_begin > sample_end");
+    const uint64_t n_pixels = static_cast<uint64_t>(rp.width) * rp.height;
+    if (rp.pixel_end == 0) rp.pixel_end = static_cast<uint32_t>(n_pixels);
+    if (rp.pixel_begin > rp.pixel_end || rp.pixel_end > n_pixels) return fail(RT_ERR_INVALID_ARG, "rt_gpu_render: illegal pixel range");
     const int n = static_cast<int>(ctx->devs.size());
     const uint32_t total = rp.sample_end - rp.sample_begin;
     uint64_t launches = 0;
-    // sample-split: device g renders [begin + g*total/n, begin + (g+1)*total/n) of every pixel
+    // sample-split: device g renders [begin + g*total/n, begin + (g+1)*total/n) of every pixel.  With fewer samples
+    // than devices the image is split instead: device g renders all samples of a contiguous range of the pixels
+    // (the other pixels of its buffer stay 0, so the same reduce(sum) merges the tiles).
+    const bool tile_split = n > 1 && total < static_cast<uint32_t>(n) && rp.mode == RT_MODE_BEAUTY;
+    const uint64_t n_px = rp.pixel_end - rp.pixel_begin;
     for (int g = 0; g < n; ++g) {
-        const uint32_t sb = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * g / n);
-        const uint32_t se = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * (g + 1) / n);
+        uint32_t sb = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * g / n);
+        uint32_t se = rp.sample_begin + static_cast<uint32_t>(static_cast<uint64_t>(total) * (g + 1) / n);
         rt_render_params local = rp;
+        if (tile_split) {
+            sb = rp.sample_begin;
+            se = rp.sample_end;
+            local.pixel_begin = rp.pixel_begin + static_cast<uint32_t>(n_px * g / n);
+            local.pixel_end = rp.pixel_begin + static_cast<uint32_t>(n_px * (g + 1) / n);
+            if (local.pixel_end == local.pixel_begin) se = sb;  // nothing for this device: zero buffer only
+        }
         if (rp.mode == RT_MODE_PRIMARY_IDS && g > 0) continue;  // ids: device 0 only
         if (ctx->text_scene) {
             if (int rc = enqueue_text_render(ctx, *ctx->devs[g], local, sb, se, launches)) return rc;

@@ -19,6 +19,7 @@ struct TextParams {
     uint32_t s0, s1;   // samples [s0, s1) of every pixel
     uint32_t k0, k1;   // Philox key
     uint32_t ids;      // 1: write the primitive index of the pixel-centre ray instead of radiance
+    uint32_t pix0, npix;  // row-major pixel range rendered by this launch (image-tile split)
 };
 
 __global__ void __launch_bounds__(128) k_text_render(TextScene s, rt::Camera cam, TextParams tp, float4 *__restrict__ accum,
@@ -40,8 +41,9 @@ __global__ void __launch_bounds__(128) k_text_render(TextScene s, rt::Camera cam
     s.lights = sh_lights;
     s.emitters = sh_emit;
 
-    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pixel >= tp.width * tp.height) return;
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= tp.npix) return;
+    const uint32_t pixel = tp.pix0 + local;
     const uint32_t py = pixel / tp.width, px = pixel - py * tp.width;
     const f3 centre = rt::camera_dir(cam, static_cast<float>(px) + 0.5f, static_cast<float>(py) + 0.5f);
     if (tp.ids) {

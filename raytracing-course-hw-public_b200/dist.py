@@ -16,6 +16,18 @@ def sample_range(samples, rank, world):
     return samples * rank // world, samples * (rank + 1) // world
 
 
+def work_split(samples, n_pixels, rank, world):
+    """(sample_begin, sample_end, pixel_begin, pixel_end) of `rank`: samples are split while there is at least one
+    per rank (every rank renders all pixels); with fewer samples than ranks the IMAGE is split into contiguous
+    pixel ranges instead and every rank renders all samples of its range (north star: "falling back to image tiles
+    for small spp").  Either way the ranks' buffers are disjoint contributions that one reduce(sum) merges."""
+    if samples >= world:
+        sb, se = sample_range(samples, rank, world)
+        return sb, se, 0, n_pixels
+    pb, pe = sample_range(n_pixels, rank, world)
+    return 0, samples, pb, pe
+
+
 class _CudaView:
     """__cuda_array_interface__ wrapper around the backend's accumulation buffer (zero copy)."""
 
@@ -48,9 +60,9 @@ def reduce_sums(tensor, dst=0):
 def render_distributed(rt, width, height, samples, seed, rank, world, device_index, max_paths_in_flight=0):
     """Render this rank's sample range on its GPU, reduce to rank 0. Returns the torch view of the sums
     (complete on rank 0 only)."""
-    sb, se = sample_range(samples, rank, world)
+    sb, se, pb, pe = work_split(samples, width * height, rank, world)
     rt.render(width, height, samples, seed=seed, sample_begin=sb, sample_end=max(se, sb),
-              max_paths_in_flight=max_paths_in_flight)
+              max_paths_in_flight=max_paths_in_flight, pixel_begin=pb, pixel_end=pe)
     t = accum_as_tensor(rt, device_index)
     return reduce_sums(t, 0)
 

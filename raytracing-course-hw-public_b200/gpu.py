@@ -95,9 +95,9 @@ class RtGpu:
         _check(lib().rt_gpu_set_profiling(self._h, int(bool(enable))), "rt_gpu_set_profiling")
 
     def render(self, width, height, samples, seed=0, sample_begin=0, sample_end=0, mode=RT_MODE_BEAUTY,
-               max_paths_in_flight=0, accumulate=False):
+               max_paths_in_flight=0, accumulate=False, pixel_begin=0, pixel_end=0):
         p = rt_render_params(width, height, samples, sample_begin, sample_end, mode, seed, max_paths_in_flight,
-                             RT_FLAG_ACCUMULATE if accumulate else 0)
+                             RT_FLAG_ACCUMULATE if accumulate else 0, pixel_begin, pixel_end)
         _check(lib().rt_gpu_render(self._h, C.byref(p)), "rt_gpu_render")
         self._last = (width, height, mode)
 

@@ -27,6 +27,24 @@ def test_sample_range_is_a_partition():
         rtdist.sample_range(10, 2, 2)
 
 
+def test_work_split_samples_then_image_tiles():
+    """Samples are split while every rank gets at least one; below that the image is split into pixel ranges
+    (north star: "falling back to image tiles for small spp").  Either way the work is a partition."""
+    n_pix = 24 * 18
+    for world in (1, 2, 3, 8):
+        for samples in (0, 1, 2, 7, 8, 100):
+            parts = [rtdist.work_split(samples, n_pix, k, world) for k in range(world)]
+            covered = np.zeros((max(samples, 1), n_pix), np.int32)
+            for sb, se, pb, pe in parts:
+                assert 0 <= sb <= se <= samples and 0 <= pb <= pe <= n_pix
+                covered[sb:se, pb:pe] += 1
+            assert (covered[:samples] == 1).all()  # every (sample, pixel) exactly once
+            if samples >= world:
+                assert all(p[2:] == (0, n_pix) for p in parts)  # sample split: all pixels on every rank
+            else:
+                assert all(p[:2] == (0, samples) for p in parts)  # tile split: all samples on every rank
+
+
 def _worker(rank, world, port, out_path):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
     import oracle_lib as O
@@ -35,13 +53,19 @@ def _worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     scene = rt_b200.SceneData.load(os.path.join(GOLDEN, "tiny.rtsc"))
-    w, h, spp, seed = 24, 18, 10, 5
-    sb, se = rtdist.sample_range(spp, rank, world)
-    mean, _ = O.render(scene, w, h, spp, rng_mode=O.RNG_PHILOX, seed=seed, sample_begin=sb, sample_end=se, n_threads=1)
-    sums = torch.from_numpy(mean * np.float32(spp))  # this rank's per-pixel sums
-    rtdist.reduce_sums(sums, 0)
+    w, h, seed = 24, 18, 5
+    merged = {}
+    for spp in (10, 1):  # 10 samples: sample split; 1 sample on 2 ranks: image-tile split
+        sb, se, pb, pe = rtdist.work_split(spp, w * h, rank, world)
+        mean, _ = O.render(scene, w, h, spp, rng_mode=O.RNG_PHILOX, seed=seed, sample_begin=sb, sample_end=se, n_threads=1)
+        sums = (mean * np.float32(spp)).reshape(w * h, 3)
+        mask = np.zeros((w * h, 1), np.float32)
+        mask[pb:pe] = 1  # the backend renders only [pb, pe); the oracle renders all pixels, so mask the rest
+        sums = torch.from_numpy((sums * mask).reshape(h, w, 3))
+        rtdist.reduce_sums(sums, 0)
+        merged[spp] = sums.numpy() / np.float32(spp)
     if rank == 0:
-        np.save(out_path, sums.numpy() / np.float32(spp))
+        np.savez(out_path, **{f"spp{k}": v for k, v in merged.items()})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -53,12 +77,13 @@ def test_two_rank_sample_split_equals_single_render(tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    out = str(tmp_path / "merged.npy")
+    out = str(tmp_path / "merged.npz")
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     merged = np.load(out)
     scene = rt_b200.SceneData.load(os.path.join(GOLDEN, "tiny.rtsc"))
-    full, _ = O.render(scene, 24, 18, 10, rng_mode=O.RNG_PHILOX, seed=5)
-    assert np.allclose(merged, full, rtol=1e-5, atol=1e-7)
+    for spp in (10, 1):
+        full, _ = O.render(scene, 24, 18, spp, rng_mode=O.RNG_PHILOX, seed=5)
+        assert np.allclose(merged[f"spp{spp}"], full, rtol=1e-5, atol=1e-7)
 
 
 def test_merge_host_sums():

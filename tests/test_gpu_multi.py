@@ -45,7 +45,7 @@ def test_single_process_multi_device_matches_one_device(golden_scene):
     assert np.allclose(img, ref, rtol=2e-6, atol=1e-7)
     assert stn["samples"] == st1["samples"] and stn["extension_rays"] == st1["extension_rays"]
     assert rgb8.shape == (h, w, 3)
-    # fewer samples than devices: some devices render nothing, the image is still complete
+    # fewer samples than devices: the image is split into pixel ranges instead (tile split), still complete
     with gpu.RtGpu(n, 0) as many:
         many.upload_scene(sc)
         many.render(w, h, 1, seed=11)

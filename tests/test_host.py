@@ -53,7 +53,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_abi.rt_bvh_node) == 40
     assert C.sizeof(_abi.rt_bvh_desc) == 32
     assert C.sizeof(_abi.rt_camera) == 52
-    assert C.sizeof(_abi.rt_render_params) == 40
+    assert C.sizeof(_abi.rt_render_params) == 48  # + pixel_begin, pixel_end (image-tile split)
     # rt_scene_desc: 8 + 52 + 12 + 12 + 4 + 12 (+pad) ... checked through a C round trip instead
     sc = rt_b200.SceneData.load(os.path.join(GOLDEN, "tiny.rtsc"))
     assert host.validate(sc) == 0
