@@ -5,9 +5,11 @@
 #define RT_REPACK_H
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "rt_gpu.h"
@@ -40,6 +42,21 @@ struct PackedScene {
 };
 
 namespace detail {
+
+// run fn(begin, end) over [0, n) on up to `max_threads` host threads (the per-node packing loops are independent)
+template <class F> inline void parallel_for(size_t n, F fn, size_t grain = 4096, unsigned max_threads = 16) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(std::min<unsigned>(hw ? hw : 1, max_threads), (n + grain - 1) / grain);
+    if (nt <= 1) {
+        fn(static_cast<size_t>(0), n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back([=] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    fn(static_cast<size_t>(0), std::min(n, chunk));
+    for (auto &x : th) x.join();
+}
 
 inline void set_box(DNode &n, bool left, const float *lo, const float *hi) {
     if (left) {
@@ -175,22 +192,25 @@ inline bool quantize_axis(const float lo[2], const float hi[2], uint32_t &word, 
 
 inline int quantize_nodes(const std::vector<DNode> &nodes, std::vector<QNode> &out) {
     out.resize(nodes.size());
-    for (size_t i = 0; i < nodes.size(); ++i) {
-        const DNode &n = nodes[i];
-        const float lo[3][2] = {{n.lminx, n.rminx}, {n.lminy, n.rminy}, {n.lminz, n.rminz}};
-        const float hi[3][2] = {{n.lmaxx, n.rmaxx}, {n.lmaxy, n.rmaxy}, {n.lmaxz, n.rmaxz}};
-        uint8_t q[3][4];
-        QNode &o = out[i];
-        for (int a = 0; a < 3; ++a)
-            if (!quantize_axis(lo[a], hi[a], o.org[a], q[a])) return RT_ERR_BAD_SCENE;
-        // one word per axis: left.min, left.max, right.min, right.max (quantize_axis's order)
-        for (int w = 0; w < 3; ++w)
-            o.q[w] = static_cast<uint32_t>(q[w][0]) | static_cast<uint32_t>(q[w][1]) << 8 |
-                     static_cast<uint32_t>(q[w][2]) << 16 | static_cast<uint32_t>(q[w][3]) << 24;
-        o.left = n.left;
-        o.right = n.right;
-    }
-    return RT_OK;
+    std::atomic<int> rc{RT_OK};
+    parallel_for(nodes.size(), [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            const DNode &n = nodes[i];
+            const float lo[3][2] = {{n.lminx, n.rminx}, {n.lminy, n.rminy}, {n.lminz, n.rminz}};
+            const float hi[3][2] = {{n.lmaxx, n.rmaxx}, {n.lmaxy, n.rmaxy}, {n.lmaxz, n.rmaxz}};
+            uint8_t q[3][4];
+            QNode &o = out[i];
+            for (int a = 0; a < 3; ++a)
+                if (!quantize_axis(lo[a], hi[a], o.org[a], q[a])) rc = RT_ERR_BAD_SCENE;
+            // one word per axis: left.min, left.max, right.min, right.max (quantize_axis's order)
+            for (int w = 0; w < 3; ++w)
+                o.q[w] = static_cast<uint32_t>(q[w][0]) | static_cast<uint32_t>(q[w][1]) << 8 |
+                         static_cast<uint32_t>(q[w][2]) << 16 | static_cast<uint32_t>(q[w][3]) << 24;
+            o.left = n.left;
+            o.right = n.right;
+        }
+    });
+    return rc;
 }
 
 // ---- 4-wide collapse ------------------------------------------------------------------------------------------
@@ -206,52 +226,71 @@ inline void children_of(const DNode &n, Child4 out[2]) {
     out[0] = Child4{n.left, {n.lminx, n.lminy, n.lminz}, {n.lmaxx, n.lmaxy, n.lmaxz}};
     out[1] = Child4{n.right, {n.rminx, n.rminy, n.rminz}, {n.rmaxx, n.rmaxy, n.rmaxz}};
 }
-// Returns the 4-wide link of binary link `link` (leaves keep their ~first_triangle link).
-inline int32_t collapse4(const std::vector<DNode> &nodes, int32_t link, int32_t null_leaf, std::vector<QNode4> &out, int &rc) {
-    if (link < 0) return link;
+// Returns the 4-wide link of binary link `link` (leaves keep their ~first_triangle link).  Only the topology is built
+// here (children and their exact boxes, recorded in `boxes`); quantise_nodes4() fills the plane bytes afterwards.
+struct Node4Boxes {
     Child4 ch[4];
-    int n = 2;
-    children_of(nodes[link], ch);
-    while (n < 4) {  // open the inner child with the largest box until four children or only leaves are left
+    int n;
+};
+inline int32_t collapse4(const std::vector<DNode> &nodes, int32_t link, int32_t null_leaf, std::vector<QNode4> &out,
+                         std::vector<Node4Boxes> &boxes) {
+    if (link < 0) return link;
+    Node4Boxes nb;
+    nb.n = 2;
+    children_of(nodes[link], nb.ch);
+    while (nb.n < 4) {  // open the inner child with the largest box until four children or only leaves are left
         int best = -1;
         float best_area = -1.0f;
-        for (int i = 0; i < n; ++i)
-            if (ch[i].link >= 0 && box_area(ch[i]) > best_area) {
-                best_area = box_area(ch[i]);
+        for (int i = 0; i < nb.n; ++i)
+            if (nb.ch[i].link >= 0 && box_area(nb.ch[i]) > best_area) {
+                best_area = box_area(nb.ch[i]);
                 best = i;
             }
         if (best < 0) break;
         Child4 two[2];
-        children_of(nodes[ch[best].link], two);
-        ch[best] = two[0];
-        ch[n++] = two[1];
+        children_of(nodes[nb.ch[best].link], two);
+        nb.ch[best] = two[0];
+        nb.ch[nb.n++] = two[1];
     }
     const int32_t idx = static_cast<int32_t>(out.size());
     out.emplace_back();
+    boxes.push_back(nb);
     int32_t links[4];
-    for (int i = 0; i < 4; ++i) links[i] = i < n ? collapse4(nodes, ch[i].link, null_leaf, out, rc) : null_leaf;
+    for (int i = 0; i < 4; ++i) links[i] = i < nb.n ? collapse4(nodes, nb.ch[i].link, null_leaf, out, boxes) : null_leaf;
     QNode4 &q = out[idx];
     std::memset(&q, 0, sizeof q);
-    for (int a = 0; a < 3; ++a) {
-        float lo[4], hi[4];
-        uint8_t ql[4] = {255, 255, 255, 255}, qh[4] = {0, 0, 0, 0};  // absent child: inverted box
-        for (int i = 0; i < n; ++i) {
-            lo[i] = ch[i].lo[a];
-            hi[i] = ch[i].hi[a];
-        }
-        if (!quantize_axis_n(lo, hi, n, q.org[a], ql, qh)) rc = RT_ERR_BAD_SCENE;
-        q.lo[a] = static_cast<uint32_t>(ql[0]) | static_cast<uint32_t>(ql[1]) << 8 | static_cast<uint32_t>(ql[2]) << 16 |
-                  static_cast<uint32_t>(ql[3]) << 24;
-        q.hi[a] = static_cast<uint32_t>(qh[0]) | static_cast<uint32_t>(qh[1]) << 8 | static_cast<uint32_t>(qh[2]) << 16 |
-                  static_cast<uint32_t>(qh[3]) << 24;
-    }
     for (int i = 0; i < 4; ++i) q.link[i] = links[i];
     return idx;
+}
+inline int quantize_nodes4(const std::vector<Node4Boxes> &boxes, std::vector<QNode4> &out) {
+    std::atomic<int> rc{RT_OK};
+    parallel_for(out.size(), [&](size_t b, size_t e) {
+        for (size_t k = b; k < e; ++k) {
+            const Node4Boxes &nb = boxes[k];
+            QNode4 &q = out[k];
+            for (int a = 0; a < 3; ++a) {
+                float lo[4], hi[4];
+                uint8_t ql[4] = {255, 255, 255, 255}, qh[4] = {0, 0, 0, 0};  // absent child: inverted box
+                for (int i = 0; i < nb.n; ++i) {
+                    lo[i] = nb.ch[i].lo[a];
+                    hi[i] = nb.ch[i].hi[a];
+                }
+                if (!quantize_axis_n(lo, hi, nb.n, q.org[a], ql, qh)) rc = RT_ERR_BAD_SCENE;
+                q.lo[a] = static_cast<uint32_t>(ql[0]) | static_cast<uint32_t>(ql[1]) << 8 | static_cast<uint32_t>(ql[2]) << 16 |
+                          static_cast<uint32_t>(ql[3]) << 24;
+                q.hi[a] = static_cast<uint32_t>(qh[0]) | static_cast<uint32_t>(qh[1]) << 8 | static_cast<uint32_t>(qh[2]) << 16 |
+                          static_cast<uint32_t>(qh[3]) << 24;
+            }
+        }
+    });
+    return rc;
 }
 
 }  // namespace detail
 
-inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &out) {
+// `formats`: which quantised node arrays to produce (the device build needs one, the host checks both)
+enum { RT_PACK_Q2 = 1, RT_PACK_Q4 = 2, RT_PACK_ALL = 3 };
+inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &out, int formats = RT_PACK_ALL) {
     out.nodes.clear();
     out.tris.assign(src.n_objects, DTri());
     out.order.assign(src.objects, src.objects + src.n_objects);
@@ -272,37 +311,45 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     int rc = RT_OK;
     out.root = detail::pack_node(src, src.root, out, 0, rc);
     if (rc) return rc;
-    if (int rq = detail::quantize_nodes(out.nodes, out.qnodes)) return rq;
+    out.qnodes.clear();
+    if (formats & RT_PACK_Q2)
+        if (int rq = detail::quantize_nodes(out.nodes, out.qnodes)) return rq;
     // 4-wide collapse; the null leaf (absent children) is one degenerate triangle appended after the real ones
     out.qnodes4.clear();
     DTri null_tri;
     std::memset(&null_tri, 0, sizeof null_tri);
     null_tri.id_last = RT_LAST_BIT;
     out.tris.push_back(null_tri);
-    const int32_t null_leaf = ~static_cast<int32_t>(out.tris.size() - 1);
-    out.root4 = detail::collapse4(out.nodes, out.root, null_leaf, out.qnodes4, rc);
+    if (formats & RT_PACK_Q4) {
+        const int32_t null_leaf = ~static_cast<int32_t>(out.tris.size() - 1);
+        std::vector<detail::Node4Boxes> boxes;
+        out.qnodes4.reserve(out.nodes.size() / 2 + 1);
+        boxes.reserve(out.nodes.size() / 2 + 1);
+        out.root4 = detail::collapse4(out.nodes, out.root, null_leaf, out.qnodes4, boxes);
+        if (int rq = detail::quantize_nodes4(boxes, out.qnodes4)) return rq;
+    }
     return rc;
 }
 
 // `rebuild_scene_bvh`: build the scene BVH with the library's SAH builder (sah_build.h) over the triangles of
 // sc.scene_bvh instead of adopting the host's tree; the light BVH is always adopted as passed.
-inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false) {
+inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false, int formats = RT_PACK_ALL) {
     if (rebuild_scene_bvh && sc.scene_bvh.n_objects > 0 && sc.scene_bvh.root != RT_NO_CHILD) {
         BuiltBvh built;
         build_sah_bvh(sc.tri_pos, sc.scene_bvh.objects, sc.scene_bvh.n_objects, built);
-        if (int rc = pack_bvh(sc, built.desc(), out.scene)) return rc;
-    } else if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene)) {
+        if (int rc = pack_bvh(sc, built.desc(), out.scene, formats)) return rc;
+    } else if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene, formats)) {
         return rc;
     }
     // light BVH: the traversal (all-hit light pdf) uses a rebuilt tree as well; the sampling list keeps the host's order
     {
         PackedBvh host_order;
-        if (int rc = pack_bvh(sc, sc.light_bvh, host_order)) return rc;
+        if (int rc = pack_bvh(sc, sc.light_bvh, host_order, formats)) return rc;
         out.light_sample = host_order.tris;
         if (rebuild_scene_bvh && sc.light_bvh.n_objects > 0 && sc.light_bvh.root != RT_NO_CHILD) {
             BuiltBvh built;
             build_sah_bvh(sc.tri_pos, sc.light_bvh.objects, sc.light_bvh.n_objects, built);
-            if (int rc = pack_bvh(sc, built.desc(), out.light)) return rc;
+            if (int rc = pack_bvh(sc, built.desc(), out.light, formats)) return rc;
         } else {
             out.light = host_order;
         }

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -510,9 +511,17 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     rt::PackedScene packed;
     const char *keep_env = std::getenv("RT_KEEP_HOST_BVH");  // A/B switch for measurements
     const bool keep = (scene->flags & RT_SCENE_KEEP_HOST_BVH) || (keep_env && std::atoi(keep_env) != 0);
-    if (int rc = rt::pack_scene(*scene, packed, !keep)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    const auto t_pack0 = std::chrono::steady_clock::now();
+    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE4 ? rt::RT_PACK_Q4 : rt::RT_PACK_Q2)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    const auto t_pack1 = std::chrono::steady_clock::now();
     for (auto &d : ctx->devs)
         if (int rc = upload_to_device(*d, *scene, packed)) return rc;
+    if (std::getenv("RT_TIMING")) {
+        const auto t_up = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "rt_gpu_upload_scene: re-pack (BVH build, collapse, quantise, attributes) %.1f ms, H2D %.1f ms\n",
+                     std::chrono::duration<double, std::milli>(t_pack1 - t_pack0).count(),
+                     std::chrono::duration<double, std::milli>(t_up - t_pack1).count());
+    }
     ctx->ray_depth = scene->ray_depth;
     ctx->have_scene = true;
     ctx->have_render = false;

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -114,37 +115,84 @@ inline void build_range(Ctx &cx, uint32_t slot, uint32_t b, uint32_t e, const Bo
     if (!force_median) {
         float best_cost = std::numeric_limits<float>::infinity();
         int best_axis = -1, best_bin = -1;
+        // one pass over the primitives fills the bins of all three axes; large ranges near the root are binned by
+        // several threads into private bins that are merged afterwards
+        struct Bins {
+            Box3 box[3][kBins];
+            uint32_t cnt[3][kBins];
+            void reset(int nbins) {
+                for (int a = 0; a < 3; ++a)
+                    for (int i = 0; i < nbins; ++i) {
+                        box[a][i].reset();
+                        cnt[a][i] = 0;
+                    }
+            }
+        };
+        const int nb = n <= 32 ? 8 : kBins;  // small ranges: fewer bins, the sweep over empty bins would dominate
+        float cmin[3], scale[3];
+        bool use[3];
+        for (int a = 0; a < 3; ++a) {
+            const float cext = cbox.hi[a] - cbox.lo[a];
+            use[a] = cext > 0.0f;
+            cmin[a] = cbox.lo[a];
+            scale[a] = use[a] ? static_cast<float>(nb) / cext : 0.0f;
+        }
+        auto bin_range = [&](uint32_t rb, uint32_t re, Bins &bins) {
+            bins.reset(nb);
+            for (uint32_t i = rb; i < re; ++i)
+                for (int a = 0; a < 3; ++a) {
+                    if (!use[a]) continue;
+                    int k = static_cast<int>((P[i].c[a] - cmin[a]) * scale[a]);
+                    k = k < 0 ? 0 : (k >= nb ? nb - 1 : k);
+                    bins.box[a][k].grow(P[i].lo, P[i].hi);
+                    ++bins.cnt[a][k];
+                }
+        };
+        Bins local_bins;  // 2.7 KB on the stack (recursion depth <= RT_STACK_SIZE)
+        Bins *bins = &local_bins;
+        if (n >= 4 * kParallelMin && depth < kParallelDepth) {
+            const unsigned hw = std::thread::hardware_concurrency();
+            const uint32_t nt = std::max(1u, std::min(hw ? hw : 1u, std::min(16u >> depth, n / kParallelMin)));
+            std::vector<std::unique_ptr<Bins>> part(nt);
+            std::vector<std::thread> th;
+            const uint32_t chunk = (n + nt - 1) / nt;
+            for (uint32_t t = 0; t < nt; ++t) {
+                part[t].reset(new Bins);
+                const uint32_t rb = b + std::min(n, t * chunk), re = b + std::min(n, (t + 1) * chunk);
+                if (t + 1 < nt) th.emplace_back([&bin_range, rb, re, &part, t] { bin_range(rb, re, *part[t]); });
+                else bin_range(rb, re, *part[t]);
+            }
+            for (auto &x : th) x.join();
+            bins->reset(nb);
+            for (uint32_t t = 0; t < nt; ++t)
+                for (int a = 0; a < 3; ++a)
+                    for (int i = 0; i < nb; ++i)
+                        if (part[t]->cnt[a][i]) {
+                            bins->box[a][i].grow(part[t]->box[a][i]);
+                            bins->cnt[a][i] += part[t]->cnt[a][i];
+                        }
+        } else {
+            bin_range(b, e, *bins);
+        }
         for (int axis = 0; axis < 3; ++axis) {
-            const float cmin = cbox.lo[axis], cext = cbox.hi[axis] - cbox.lo[axis];
-            if (!(cext > 0.0f)) continue;
-            const float scale = static_cast<float>(kBins) / cext;
-            Box3 bins[kBins];
-            uint32_t cnt[kBins];
-            for (int i = 0; i < kBins; ++i) {
-                bins[i].reset();
-                cnt[i] = 0;
-            }
-            for (uint32_t i = b; i < e; ++i) {
-                int k = static_cast<int>((P[i].c[axis] - cmin) * scale);
-                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-                bins[k].grow(P[i].lo, P[i].hi);
-                ++cnt[k];
-            }
+            if (!use[axis]) continue;
+            const Box3 *bx = bins->box[axis];
+            const uint32_t *cnt = bins->cnt[axis];
             float right_area[kBins];
             uint32_t right_cnt[kBins];
             Box3 acc;
             acc.reset();
             uint32_t c = 0;
-            for (int i = kBins - 1; i > 0; --i) {
-                if (cnt[i]) acc.grow(bins[i]);
+            for (int i = nb - 1; i > 0; --i) {
+                if (cnt[i]) acc.grow(bx[i]);
                 c += cnt[i];
                 right_area[i] = c ? acc.area() : 0.0f;
                 right_cnt[i] = c;
             }
             acc.reset();
             c = 0;
-            for (int i = 0; i < kBins - 1; ++i) {  // split after bin i
-                if (cnt[i]) acc.grow(bins[i]);
+            for (int i = 0; i < nb - 1; ++i) {  // split after bin i
+                if (cnt[i]) acc.grow(bx[i]);
                 c += cnt[i];
                 if (c == 0 || right_cnt[i + 1] == 0) continue;
                 const float cost = static_cast<float>(c) * acc.area() + static_cast<float>(right_cnt[i + 1]) * right_area[i + 1];
@@ -159,12 +207,12 @@ inline void build_range(Ctx &cx, uint32_t slot, uint32_t b, uint32_t e, const Bo
         const float leaf_cost = static_cast<float>(n) * node_area;
         if (best_axis >= 0 && (n > kMaxLeaf || kTraversalCost * node_area + best_cost < leaf_cost)) {
             const int axis = best_axis;
-            const float cmin = cbox.lo[axis], scale = static_cast<float>(kBins) / (cbox.hi[axis] - cbox.lo[axis]);
+            const float pmin = cmin[axis], pscale = scale[axis];
             lbox.reset(); rbox.reset(); lcb.reset(); rcb.reset();
             uint32_t i = b, j = e;
             while (i < j) {  // in-place partition by bin index
-                int k = static_cast<int>((P[i].c[axis] - cmin) * scale);
-                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                int k = static_cast<int>((P[i].c[axis] - pmin) * pscale);
+                k = k < 0 ? 0 : (k >= nb ? nb - 1 : k);
                 if (k <= best_bin) {
                     lbox.grow(P[i].lo, P[i].hi);
                     lcb.grow(P[i].c, P[i].c);

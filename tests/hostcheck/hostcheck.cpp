@@ -167,6 +167,25 @@ int hc_primary_ids_q4(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *
     return 0;
 }
 
+// Wall time of the re-pack phases (ms): out[0] SAH build, out[1] pack_bvh of the scene tree (triangles, nodes, both
+// quantisations, collapse), out[2] whole pack_scene with rebuild.
+int hc_pack_timing(const rt_scene_desc *sc, double *out) {
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t0 = clk::now();
+    BuiltBvh built;
+    build_sah_bvh(sc->tri_pos, sc->scene_bvh.objects, sc->scene_bvh.n_objects, built);
+    auto t1 = clk::now();
+    PackedBvh pb;
+    if (int rc = pack_bvh(*sc, built.desc(), pb)) return rc;
+    auto t2 = clk::now();
+    PackedScene ps;
+    if (int rc = pack_scene(*sc, ps, true)) return rc;
+    auto t3 = clk::now();
+    out[0] = ms(t0, t1); out[1] = ms(t1, t2); out[2] = ms(t2, t3);
+    return 0;
+}
+
 // Quantised-node invariants over the whole scene BVH.  out[0] = nodes, out[1] = planes whose decoded position
 // (exact arithmetic: org + q * cell) is on the wrong side of the exact plane (must be 0), out[2] = planes with
 // less than 1/128 cell of slack (must be 0: the packer keeps 1/64), out[3..4] = summed surface area of the exact
