@@ -2,9 +2,11 @@
 //
 //   k_generate   N paths: Philox pixel jitter -> camera ray (gen_ray, raytracer.h:527-538)
 //   for bounce b in [0, ray_depth):
-//     k_extend   closest-hit BVH traversal of queue b (cast_ray -> BVH::intersect_ray, bvh.h:170-235)
-//     k_shade    hit data + shade() state transition (raytracer.h:555-591), light pdf traversal,
-//                survivors compacted into queue b+1 with warp-aggregated (__ballot/__popc) appends
+//     k_extend   closest-hit BVH traversal of queue b (cast_ray -> BVH::intersect_ray, bvh.h:170-235); for a
+//                "pending" ray first the all-hit traversal of the light BVH (bvh_mix_dist::pdf, raytracer.h:363)
+//     k_shade    resolve the previous bounce with that light pdf, hit data + shade() state transition
+//                (raytracer.h:555-591), survivors compacted into queue b+1 with warp-aggregated
+//                (__ballot/__popc) appends
 //   k_accumulate per-sample NaN scrub + per-pixel float sums (render_pixel, raytracer.h:607-627)
 //
 // Path state is SoA of float4 (128-bit coalesced loads/stores), ping-ponged between queue b and b+1:
@@ -13,6 +15,7 @@
 //   q_thr = (throughput.rgb [x f_cos when pending], p_partial >= 0 when the path's pdf still needs the light
 //            pdf of this ray ("pending", also bit 31 of the sample index), else -1)
 //   hit   = (t, beta, gamma, BVH-order triangle index bits or -1)      written by extend, read by shade
+//   lpdf  = light pdf of the queued ray                                 written by extend for pending rays
 //   rad   = per-path radiance accumulator, indexed by the path's fixed slot (no atomics: one owner)
 // extend and shade are persistent: grid = SMs x resident CTAs, each warp pulls 32 queue entries at a
 // time from a device counter, so no host round trip is needed to size a launch.

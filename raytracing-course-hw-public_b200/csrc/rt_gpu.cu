@@ -1,9 +1,10 @@
 // rt_gpu.cu — implementation of the C ABI in include/rt_gpu.h on top of the wavefront kernels.
 //
 // One DeviceState per GPU (own stream, own copy of the scene, own queues).  A render splits the
-// sample range across the devices of the handle (sample-split), every device runs
-// its batches asynchronously on its stream, and for more than one device the per-pixel float sums
-// are merged with a single ncclReduce(sum) to device 0.  NCCL is resolved with dlopen at the first
+// sample range across the devices of the handle (sample-split; image tiles when there
+// are fewer samples than devices), every device runs its batches asynchronously on its stream, and
+// for more than one device the per-pixel float sums are merged with a single ncclReduce(sum) to
+// device 0.  rt_gpu_upload_scene re-packs on the host (own SAH tree, 4-wide collapse, quantisation).  NCCL is resolved with dlopen at the first
 // multi-device create so that single-device users never need the library.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
