@@ -189,18 +189,19 @@ RT_HD bool tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float min_dst, float &t, flo
 }
 
 // ---- quantised node (QNode, rt_types.h): both child slab tests from one 32-byte record --------------------
-// Plane byte q of a word -> the float 1 + q * 2^-15 (q placed in mantissa bits 8..15 by one PRMT), so that
-//   t(q) = (org + q * cell - o) / d = fma(1 + q * 2^-15, A, B)   with  A = 2^15 * cell / d,  B = (org - o) / d - A
-// costs one PRMT + one FFMA per plane and no integer->float conversion.  A is 128 x the node's extent in ray
-// space, so B carries an absolute rounding error of ~2^-9 cell; the packer keeps a 1/64-cell margin for it.
-// `one` = 0x3F800000, which k_extend receives as a kernel ARGUMENT: PRMT takes one immediate, and it has to be the
-// selector — when the compiler sees the constant it makes that the immediate and re-materialises all the selectors
-// in registers (14 extra moves per node step).
+// Plane byte q of a word -> the float 1 + q * 2^-16 (q added into mantissa bits 7..14), so that
+//   t(q) = (org + q * cell - o) / d = fma(1 + q * 2^-16, A, B)   with  A = 2^16 * cell / d,  B = (org - o) / d - A
+// costs one byte-dot-product + one FFMA per plane and no integer->float conversion.  The extraction is a DP4A
+// (`one + byte_K(w) * 0x80`), not a byte permute: k_extend is bound by the ALU pipe (PRMT / FMNMX / SEL: 67 % of
+// peak against 25 % for the FMA pipe, profiles/r1_v10_k_extend_ncu_full.csv), and IDP.4A issues on the FMA pipe.
+// A is 256 x the node's extent in ray space, so B carries an absolute rounding error of ~2^-8 cell; the packer
+// keeps a 1/64-cell margin for it.
+// `one` = 0x3F800000, which k_extend receives as a kernel ARGUMENT so that it stays in a register.
 template <int K> RT_HD float qplane(uint32_t w, uint32_t one) {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(w, one, 0x7604u | (K << 4)));
+    return __uint_as_float(__dp4a(w, 0x80u << (8 * K), one));
 #else
-    return u2f(one | (((w >> (8 * K)) & 255u) << 8));
+    return u2f(one + (((w >> (8 * K)) & 255u) << 7));
 #endif
 }
 RT_HD uint32_t qnode_one() { return 0x3F800000u; }  // the kernel gets it as an argument instead
@@ -232,9 +233,9 @@ RT_HD uint32_t swz(uint32_t w, uint32_t sel) {
 
 RT_HD NodeTest qnode_test(const uint32_t ox, const uint32_t oy, const uint32_t oz, const uint32_t q0, const uint32_t q1,
                           const uint32_t q2, f3 idir, f3 ood, RaySwz sw, uint32_t one, float eps, float best_t) {
-    const float ax = u2f((ox << 23) + 0x07800000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
-    const float ay = u2f((oy << 23) + 0x07800000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
-    const float az = u2f((oz << 23) + 0x07800000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
+    const float ax = u2f((ox << 23) + 0x08000000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
+    const float ay = u2f((oy << 23) + 0x08000000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
+    const float az = u2f((oz << 23) + 0x08000000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
     const uint32_t wx = swz(q0, sw.x), wy = swz(q1, sw.y), wz = swz(q2, sw.z);
     // slab test of both children (bvh.h:137-152): entry = max of the three near planes, exit = min of the three far
     // planes, interval clipped to [eps, best_t] (hit <=> entry <= exit): visits the boxes
@@ -328,9 +329,9 @@ template <int C> RT_HD float q4_entry(uint32_t nx, uint32_t ny, uint32_t nz, uin
 RT_HD Node4Test qnode4_test(const uint32_t ox, const uint32_t oy, const uint32_t oz, const uint32_t lox, const uint32_t loy,
                             const uint32_t loz, const uint32_t hix, const uint32_t hiy, const uint32_t hiz, f3 idir, f3 ood,
                             uint32_t one, float eps, float best_t) {
-    const float ax = u2f((ox << 23) + 0x07800000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
-    const float ay = u2f((oy << 23) + 0x07800000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
-    const float az = u2f((oz << 23) + 0x07800000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
+    const float ax = u2f((ox << 23) + 0x08000000u) * idir.x, bx = fmaf(u2f(ox), idir.x, -ood.x) - ax;
+    const float ay = u2f((oy << 23) + 0x08000000u) * idir.y, by = fmaf(u2f(oy), idir.y, -ood.y) - ay;
+    const float az = u2f((oz << 23) + 0x08000000u) * idir.z, bz = fmaf(u2f(oz), idir.z, -ood.z) - az;
     const bool px = !(idir.x < 0.0f), py = !(idir.y < 0.0f), pz = !(idir.z < 0.0f);
     const uint32_t nx = px ? lox : hix, fx = px ? hix : lox;
     const uint32_t ny = py ? loy : hiy, fy = py ? hiy : loy;

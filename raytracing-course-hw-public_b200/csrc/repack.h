@@ -148,7 +148,7 @@ inline bool quantize_axis_n(const float *lo, const float *hi, int n, uint32_t &w
     const double ext = static_cast<double>(mx) - static_cast<double>(mn);
     int e_first = 1;
     if (ext > 0.0) e_first = std::max(1, std::ilogb(ext / 255.0) + 127 - 1);
-    for (int e = e_first; e <= 239; ++e) {  // smallest cell that covers the extent in 255 steps
+    for (int e = e_first; e <= 238; ++e) {  // smallest cell that covers the extent in 255 steps (e + 16 stays a finite exponent)
         const double cell = std::ldexp(1.0, e - 127);
         const uint32_t eb = static_cast<uint32_t>(e);
         // origin = the float whose bits are (23 high bits chosen here | bit 8 = 0 | e); it has to be
