@@ -117,6 +117,9 @@ typedef struct rt_scene_desc {
     uint32_t n_materials;
     uint32_t n_textures;
     uint32_t flags;           /* RT_SCENE_* bits; 0 = defaults */
+    uint32_t env_texture;     /* 0: constant sky = bg_color (HEAD: USE_ENV_MAP = false, src/config.h:36).  k + 1:
+                                 textures[k] is the equirectangular environment map `Scene::bg`, looked up by
+                                 Scene::bg_at (src/scene.h:83-89) and scaled by bg_color */
     uint64_t texel_bytes;
     /* per-triangle arrays in scene.objects order (Object, geometry.h:639-659) */
     const float *tri_pos;          /* n_tris*9: a,b,c            */

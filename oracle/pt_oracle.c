@@ -648,8 +648,20 @@ static v3 trace_ray(const ctx_t *cx, rng_t *rng, ray_t ray, unsigned max_depth, 
         hit_t h = to_intersection_info(cx, &res, ray);
         return shade(cx, rng, ray, &h, max_depth - 1, bounce, st);
     }
-    /* Scene::bg_at with the 1x1 white `bg` texture = bg_color * (1,1,1), scene.h:83-89 */
-    return mul(V(sc->bg_color[0], sc->bg_color[1], sc->bg_color[2]), V(1, 1, 1));
+    /* Scene::bg_at, scene.h:83-89.  At HEAD `bg` is the 1x1 white texture (USE_ENV_MAP = false, config.h:36):
+     * bg_color * (1,1,1).  With an environment map: bg_color * bg.sample({x, y}, 2.2f).rgb() where
+     *   x = 0.5 + 0.5 * atan2(dir.z, dir.x) / pi_v<float>,  y = 0.5 - asin(dir.y) / pi_v<float>
+     * — the literals 0.5 are doubles: x is evaluated in double from the float atan2 (0.5 * atan2 promotes first), y
+     * divides float by float and only then promotes for the subtraction; both are rounded to float on assignment. */
+    v3 bgc = V(sc->bg_color[0], sc->bg_color[1], sc->bg_color[2]);
+    if (sc->env_texture == 0) return mul(bgc, V(1, 1, 1));
+    {
+        const float pi_f = 3.14159265358979323846f;
+        float x = (float)(0.5 + 0.5 * (double)atan2f(ray.dir.z, ray.dir.x) / (double)pi_f);
+        float y = (float)(0.5 - (double)(asinf(ray.dir.y) / pi_f));
+        c4 c = tex_sample(cx, (int32_t)sc->env_texture - 1, x, y, 1, 0);
+        return mul(bgc, V(c.r, c.g, c.b));
+    }
 }
 
 /* gen_ray (jittered), raytracer.h:527-538 */

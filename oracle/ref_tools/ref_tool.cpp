@@ -39,6 +39,9 @@ static Scene load(const char *path, unsigned w, unsigned h, unsigned spp) {
     // mirrors src/main.cpp:27-34
     Scene scene = parse_gltf_scene(std::filesystem::path(path), static_cast<float>(w) / h);
     scene.bg_color = {ENV_MAP_INTENSITY, ENV_MAP_INTENSITY, ENV_MAP_INTENSITY};
+    // main.cpp:29-31 loads ENV_MAP_PATH when the compile-time USE_ENV_MAP is set; the harness takes the path from the
+    // environment instead so that Scene::bg_at (scene.h:83-89) can be exercised without touching config.h
+    if (const char *env = std::getenv("RT_ENV_MAP")) scene.bg = geometry::Texture::load_img(env);
     scene.camera.width = w;
     scene.camera.height = h;
     scene.samples = spp;

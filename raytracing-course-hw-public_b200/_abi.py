@@ -37,7 +37,7 @@ RTSC_HEADER = np.dtype([
     ("magic", "S8"), ("abi_version", "<u4"), ("n_tris", "<u4"),
     ("cam_position", "<f4", 3), ("cam_right", "<f4", 3), ("cam_up", "<f4", 3), ("cam_forward", "<f4", 3),
     ("fov_x", "<f4"), ("bg_color", "<f4", 3), ("eps", "<f4"), ("min_roughness", "<f4"), ("vndf_factor", "<f4"),
-    ("ray_depth", "<u4"), ("n_materials", "<u4"), ("n_textures", "<u4"), ("has_tangents", "<u4"), ("_pad", "<u4"),
+    ("ray_depth", "<u4"), ("n_materials", "<u4"), ("n_textures", "<u4"), ("has_tangents", "<u4"), ("env_texture", "<u4"),
     ("texel_bytes", "<u8"),
     ("scene_n_nodes", "<u4"), ("scene_root", "<u4"), ("scene_n_objects", "<u4"),
     ("light_n_nodes", "<u4"), ("light_root", "<u4"), ("light_n_objects", "<u4"),
@@ -64,7 +64,8 @@ class rt_scene_desc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("n_tris", C.c_uint32), ("camera", rt_camera), ("bg_color", C.c_float * 3),
         ("eps", C.c_float), ("min_roughness", C.c_float), ("vndf_factor", C.c_float), ("ray_depth", C.c_uint32),
-        ("n_materials", C.c_uint32), ("n_textures", C.c_uint32), ("flags", C.c_uint32), ("texel_bytes", C.c_uint64),
+        ("n_materials", C.c_uint32), ("n_textures", C.c_uint32), ("flags", C.c_uint32), ("env_texture", C.c_uint32),
+        ("texel_bytes", C.c_uint64),
         ("tri_pos", C.c_void_p), ("tri_normals", C.c_void_p), ("tri_uv", C.c_void_p), ("tri_tangents", C.c_void_p),
         ("tri_material", C.c_void_p), ("materials", C.c_void_p), ("textures", C.c_void_p), ("texels", C.c_void_p),
         ("scene_bvh", rt_bvh_desc), ("light_bvh", rt_bvh_desc),
@@ -129,6 +130,7 @@ class SceneData:
         self.min_roughness = np.float32(0.04)             # config.h:20
         self.vndf_factor = np.float32(1.0) / np.float32(3)  # config.h:26
         self.ray_depth = 8                                # config.h:17
+        self.env_texture = 0                              # 0 = constant sky; k + 1 = textures[k] is Scene::bg
         self.tri_pos = np.zeros((0, 3, 3), np.float32)
         self.tri_normals = np.zeros((0, 3, 3), np.float32)
         self.tri_uv = np.zeros((0, 3, 2), np.float32)
@@ -175,6 +177,7 @@ class SceneData:
         d.ray_depth = int(self.ray_depth)
         d.n_materials = len(self.materials)
         d.n_textures = len(self.textures)
+        d.env_texture = int(self.env_texture)
         d.texel_bytes = int(self.texels.size)
         d.tri_pos = _ptr(self.tri_pos)
         d.tri_normals = _ptr(self.tri_normals)
@@ -208,6 +211,7 @@ class SceneData:
         h["ray_depth"] = self.ray_depth
         h["n_materials"], h["n_textures"] = len(self.materials), len(self.textures)
         h["has_tangents"] = 0 if self.tri_tangents is None else 1
+        h["env_texture"] = self.env_texture
         h["texel_bytes"] = self.texels.size
         h["scene_n_nodes"], h["scene_root"] = len(self.scene_bvh.nodes), self.scene_bvh.root
         h["scene_n_objects"] = len(self.scene_bvh.objects)
@@ -233,6 +237,7 @@ class SceneData:
         s.fov_x, s.bg_color = np.float32(h["fov_x"]), h["bg_color"].copy()
         s.eps, s.min_roughness = np.float32(h["eps"]), np.float32(h["min_roughness"])
         s.vndf_factor, s.ray_depth = np.float32(h["vndf_factor"]), int(h["ray_depth"])
+        s.env_texture = int(h["env_texture"])
         off = [RTSC_HEADER.itemsize]
 
         def take(dtype, count):

@@ -32,7 +32,7 @@ def main(argv=None):
             scene = textscene.load_text_scene(argv[1])
             width, height, samples = width or scene.width, height or scene.height, samples or scene.samples
         else:
-            scene = gltf.load_gltf(argv[1], width / height)
+            scene = gltf.load_gltf(argv[1], width / height, env_map=os.environ.get("RT_ENV_MAP") or None)
         mean, stats = run_raytracer(scene, width, height, samples, seed=int(os.environ.get("RT_SEED", "0")),
                                     n_gpus=int(os.environ.get("RT_GPUS", "1")))
         host.write_ppm(argv[5], host.tonemap_rgb8(mean))

@@ -586,6 +586,18 @@ RT_HD f4 tex_sample(const DScene &s, const float *lut, int32_t tex, float u, flo
     return r;
 }
 
+// Scene::bg_at, scene.h:83-89: bg_color * bg.sample((x, y), 2.2) with the equirectangular coordinates
+// x = 0.5 + 0.5 atan2(d.z, d.x) / pi, y = 0.5 - asin(d.y) / pi.  At HEAD `bg` is the 1x1 white texture (USE_ENV_MAP =
+// false, config.h:36), i.e. the constant bg_color: env_tex < 0.
+RT_HD f3 bg_at(const DScene &s, const float *lut, f3 d) {
+    const f3 bg = mk3(s.bg[0], s.bg[1], s.bg[2]);
+    if (s.env_tex < 0) return bg;
+    const float x = 0.5f + 0.5f * atan2f(d.z, d.x) * RT_INV_PI;
+    const float y = 0.5f - asinf(d.y) * RT_INV_PI;
+    const f4 c = tex_sample(s, lut, s.env_tex, x, y, true);
+    return bg * mk3(c.x, c.y, c.z);
+}
+
 // ray_intersection_info, bvh.h:18-29 (normals already flipped towards the ray, bvh.h:111-112)
 struct Surface {
     f3 ng, ns;     // geometric / shading normal
@@ -807,8 +819,8 @@ enum ShadeStep { SHADE_END = 0, SHADE_PASS = 1, SHADE_SAMPLED = 2 };
 //   SHADE_SAMPLED a direction was sampled; call shade_finish with the light pdf of (mid.pos, mid.dir)
 RT_HD ShadeStep shade_begin(const DScene &s, const float *lut, const RngKey &key, uint32_t bounce, bool last_bounce,
                             const Hit &h, f3 &o, const f3 &d, const f3 &thr, f3 &radiance, ShadeMid &mid) {
-    if (h.tri < 0) {  // miss: Scene::bg_at with the constant white environment, scene.h:83-89
-        radiance = radiance + thr * mk3(s.bg[0], s.bg[1], s.bg[2]);
+    if (h.tri < 0) {  // miss: Scene::bg_at, scene.h:83-89
+        radiance = radiance + thr * bg_at(s, lut, d);
         return SHADE_END;
     }
     mid.sf = make_surface(s, lut, h, d);

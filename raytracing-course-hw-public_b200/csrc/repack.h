@@ -446,6 +446,7 @@ inline void fill_scene_constants(const rt_scene_desc &sc, const PackedScene &p, 
         d.cam_fwd[k] = sc.camera.forward[k];
     }
     d.fov_x = sc.camera.fov_x;
+    d.env_tex = static_cast<int32_t>(sc.env_texture) - 1;  // 0 = constant sky
 }
 
 }  // namespace rt

@@ -133,6 +133,7 @@ struct DScene {
     uint32_t ray_depth;
     float eps, min_roughness, vndf_factor;
     float bg[3];
+    int32_t env_tex;  // -1: constant sky; else the equirectangular environment map (Scene::bg, scene.h:81)
     float cam_pos[3], cam_right[3], cam_up[3], cam_fwd[3];
     float fov_x;
 };

@@ -130,10 +130,12 @@ def _load_texture(path):
 _COMPONENT = {5121: np.uint8, 5123: np.uint16, 5125: np.uint32}
 
 
-def load_gltf(path, aspect_ratio, build_bvh=True):
+def load_gltf(path, aspect_ratio, build_bvh=True, env_map=None):
     """parse_gltf_scene(path, ar) + RaytracerStaticContext (both BVH builds) -> SceneData.
 
-    `aspect_ratio` is width/height as the CLI passes it (src/main.cpp:27)."""
+    `aspect_ratio` is width/height as the CLI passes it (src/main.cpp:27).  `env_map`: image file used as the
+    equirectangular environment map `Scene::bg` (what main.cpp:29-31 loads when USE_ENV_MAP is compiled in; None =
+    HEAD's constant white sky)."""
     with open(path) as f:
         doc = json.load(f)
     base = os.path.dirname(os.path.abspath(path))
@@ -305,6 +307,11 @@ def load_gltf(path, aspect_ratio, build_bvh=True):
     else:
         s.tri_tangents = np.zeros((0, 3, 3), F)
     s.materials = np.array(materials, MATERIAL_DTYPE) if materials else np.zeros(0, MATERIAL_DTYPE)
+    if env_map is not None:
+        env = _load_texture(env_map)
+        if env.shape[0] * env.shape[1] > 1 or not (env[0, 0, :3] == 255).all():  # 1x1 white = HEAD's constant sky
+            tex_images = tex_images + [env]
+            s.env_texture = len(tex_images)
     tex = np.zeros(len(tex_images), TEXTURE_DTYPE)
     blobs, off = [], 0
     for i, im in enumerate(tex_images):

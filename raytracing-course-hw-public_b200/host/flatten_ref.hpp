@@ -116,6 +116,22 @@ inline void flatten(const Scene &scene, const RaytracerStaticContext &ctx, FlatS
                 out.texels.push_back(static_cast<uint8_t>(std::lround(c.val[k] * 255.0f)));  // inverse of geometry.h:593
     }
 
+    // Scene::bg (scene.h:81): the 1x1 WHITE_TEXTURE at HEAD (USE_ENV_MAP = false); a host that loads an environment
+    // map into it (main.cpp:29-31) gets it appended as one more texture and referenced by env_texture
+    uint32_t env_texture = 0;
+    const bool white_1x1 = scene.bg.data.size() == 1 && scene.bg.data[0].val[0] == 1.0f && scene.bg.data[0].val[1] == 1.0f &&
+                           scene.bg.data[0].val[2] == 1.0f;
+    if (!scene.bg.data.empty() && !white_1x1) {
+        rt_texture rt;
+        rt.width = scene.bg.width;
+        rt.height = scene.bg.height;
+        rt.offset = out.texels.size();
+        out.textures.push_back(rt);
+        for (const geometry::color4 &c : scene.bg.data)
+            for (int k = 0; k < 4; ++k) out.texels.push_back(static_cast<uint8_t>(std::lround(c.val[k] * 255.0f)));
+        env_texture = static_cast<uint32_t>(out.textures.size());
+    }
+
     rt_scene_desc &d = out.desc;
     std::memset(&d, 0, sizeof d);
     d.abi_version = RT_GPU_ABI_VERSION;
@@ -134,6 +150,7 @@ inline void flatten(const Scene &scene, const RaytracerStaticContext &ctx, FlatS
     d.ray_depth = scene.ray_depth;
     d.n_materials = static_cast<uint32_t>(out.materials.size());
     d.n_textures = static_cast<uint32_t>(out.textures.size());
+    d.env_texture = env_texture;
     d.texel_bytes = out.texels.size();
     d.tri_pos = out.tri_pos.data();
     d.tri_normals = out.tri_normals.data();

@@ -10,6 +10,8 @@
 // Optional environment (additions; the 5-argument form needs none of them):
 //   RT_GPUS   number of GPUs of this box to split the samples over (default 1)
 //   RT_SEED   Philox seed (default 0)
+//   RT_ENV_MAP  image file used as the equirectangular environment map Scene::bg (the run-time form of the
+//             reference's compile-time USE_ENV_MAP / ENV_MAP_PATH, src/config.h:35-37)
 #define STB_IMAGE_IMPLEMENTATION
 
 #include <cstdio>
@@ -50,6 +52,8 @@ int main(int argc, char **argv) try {
 
     Scene scene = parse_gltf_scene(std::filesystem::path(argv[1]), static_cast<float>(width) / height);
     scene.bg_color = {ENV_MAP_INTENSITY, ENV_MAP_INTENSITY, ENV_MAP_INTENSITY};
+    if constexpr (USE_ENV_MAP) scene.bg = geometry::Texture::load_img(ENV_MAP_PATH);  // main.cpp:29-31
+    if (const char *env = std::getenv("RT_ENV_MAP")) scene.bg = geometry::Texture::load_img(env);
     scene.camera.width = width;
     scene.camera.height = height;
     scene.samples = samples;

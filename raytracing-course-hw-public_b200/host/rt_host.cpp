@@ -31,6 +31,7 @@ struct RtscHeader {
     uint32_t n_materials;
     uint32_t n_textures;
     uint32_t has_tangents;
+    uint32_t env_texture;  // was padding: 0 in older files = constant sky
     uint64_t texel_bytes;
     uint32_t scene_n_nodes, scene_root, scene_n_objects;
     uint32_t light_n_nodes, light_root, light_n_objects;
@@ -194,6 +195,7 @@ int rt_scene_validate(const rt_scene_desc *s) {
     if (s->n_tris && (!s->tri_pos || !s->tri_normals || !s->tri_uv || !s->tri_material)) return RT_ERR_BAD_SCENE;
     if (s->n_materials && !s->materials) return RT_ERR_BAD_SCENE;
     if (s->n_textures && (!s->textures || !s->texels)) return RT_ERR_BAD_SCENE;
+    if (s->env_texture > s->n_textures) return RT_ERR_BAD_SCENE;
     for (uint32_t i = 0; i < s->n_tris; ++i)
         if (s->tri_material[i] >= s->n_materials) return RT_ERR_BAD_SCENE;
     for (uint32_t i = 0; i < s->n_materials; ++i) {
@@ -228,6 +230,7 @@ int rt_scene_save(const rt_scene_desc *s, const char *path) {
     h.n_materials = s->n_materials;
     h.n_textures = s->n_textures;
     h.has_tangents = s->tri_tangents ? 1u : 0u;
+    h.env_texture = s->env_texture;
     h.texel_bytes = s->texel_bytes;
     h.scene_n_nodes = s->scene_bvh.n_nodes;
     h.scene_root = s->scene_bvh.root;
@@ -270,6 +273,7 @@ int rt_scene_load(const char *path, rt_scene_desc **out) {
     d.ray_depth = h.ray_depth;
     d.n_materials = h.n_materials;
     d.n_textures = h.n_textures;
+    d.env_texture = h.env_texture;
     d.texel_bytes = h.texel_bytes;
     d.scene_bvh.n_nodes = h.scene_n_nodes;
     d.scene_bvh.root = h.scene_root;

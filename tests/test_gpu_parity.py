@@ -47,7 +47,7 @@ def test_primary_ids_big_scene(rt, manifest, big_scene):
     assert (ids == ref).mean() >= 0.999
 
 
-@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.02), ("small_lights", 0.08), ("texall", 0.6)])
+@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.02), ("small_lights", 0.08), ("texall", 0.6), ("tiny_env", 0.02)])
 def test_paths_follow_oracle(name, tol_frac, rt, manifest, golden_scene):
     """Same Philox keys -> same paths. texall contains alpha = 0.0016 near-mirrors whose GGX D term is
     ill-conditioned in float32 in the reference's own formula (1e-2 relative noise between ANY two
@@ -85,7 +85,7 @@ def _statistical(rt, scene, name, w, h, hi, spp):
     return err, control, mae, mae_control
 
 
-@pytest.mark.parametrize("name", ["tiny", "small_lights", "texall"])
+@pytest.mark.parametrize("name", ["tiny", "small_lights", "texall", "tiny_env"])
 def test_statistical_parity_small(name, rt, manifest, golden_scene):
     m = manifest["scenes"][name]
     w, h, hi = m["width"], m["height"], m["hi_spp"]

@@ -28,7 +28,7 @@ def assert_same_scene(a, b):
     for k in ("camera_position", "camera_right", "camera_up", "camera_forward", "fov_x", "bg_color", "eps",
               "min_roughness", "vndf_factor"):
         assert np.array_equal(np.asarray(getattr(a, k)), np.asarray(getattr(b, k))), k
-    assert a.ray_depth == b.ray_depth
+    assert a.ray_depth == b.ray_depth and a.env_texture == b.env_texture
     assert a.scene_bvh.root == b.scene_bvh.root and a.light_bvh.root == b.light_bvh.root
 
 
@@ -71,6 +71,21 @@ def test_python_loader_and_bvh_build_match_reference_flattening(name, scene_dir,
     m = manifest["scenes"][name]
     mine = gltf.load_gltf(scene_dir(name), m["width"] / m["height"])
     assert_same_scene(golden_scene(name), mine)
+
+
+def test_environment_map_loader_matches_reference_flattening(scene_dir, manifest, golden_scene):
+    """Scene::bg as an equirectangular texture (main.cpp:29-31): the Python loader appends it exactly like the
+    reference-hosted flattener; the RTSC container carries env_texture."""
+    m = manifest["scenes"]["tiny_env"]
+    mine = gltf.load_gltf(scene_dir("tiny"), m["width"] / m["height"], env_map=os.path.join(GOLDEN, m["env_map"]))
+    ref = golden_scene("tiny_env")
+    assert ref.env_texture == 1 and mine.env_texture == ref.env_texture
+    assert_same_scene(ref, mine)
+    white = gltf.load_gltf(scene_dir("tiny"), 1.0)
+    assert white.env_texture == 0 and len(white.textures) == len(mine.textures) - 1
+    d = ref.desc()
+    d.env_texture = 7
+    assert host.lib().rt_scene_validate(C.byref(d)) == -7  # RT_ERR_BAD_SCENE: env_texture > n_textures
 
 
 @pytest.mark.skipif(not O.have_ref_tool(), reason="oracle/_ref not built (reference sources absent)")
@@ -282,7 +297,7 @@ def test_device_hit_data_matches_reference(name, hc, manifest, golden_scene):
 
 
 @pytest.mark.parametrize("rebuild", [0, 1])
-@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.01), ("small_lights", 0.02)])
+@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.01), ("small_lights", 0.02), ("tiny_env", 0.01)])
 def test_device_math_follows_oracle_paths(name, tol_frac, rebuild, hc, manifest, golden_scene):
     """Same Philox keys -> same paths: per-pixel means agree to float noise for all but the few pixels where a
     rounding difference flipped a discrete decision.  `rebuild`: with the library's own SAH tree instead of the
