@@ -141,7 +141,21 @@ constexpr int kMinSearching = RT_EXT_MIN_SEARCH;
 #define RT_EXT_STEPS_PER_VOTE 3  // 1 / 2 / 3 / 4 -> 103.4 / 100.4 / 99.3 / 100.4 ms of k_extend per 128 spp
 #endif
 constexpr int kStepsPerVote = RT_EXT_STEPS_PER_VOTE;
+#ifndef RT_EXT_STEP_ORDER
+#define RT_EXT_STEP_ORDER 0  // 0: node, pop, postpone   1: pop, node, postpone   2: pop, node, postpone, pop   3: pop, postpone, node, pop, postpone
+#endif
+#ifndef RT_EXT_INLINE_LMODE
+#define RT_EXT_INLINE_LMODE 1  // 1: a lane whose light-pdf traversal ends goes on into the scene BVH in the same step
+#endif
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+#if RT_EXT_WIDE4
+#define RT_NODES(b) (b).qnodes4
+#define RT_ROOT(b) (b).root4
+#else
+#define RT_NODES(b) (b).qnodes
+#define RT_ROOT(b) (b).root
+#endif
+#define RT_ROOT_OF(b) RT_ROOT(b)
 
 // MUFU.RCP (1 ulp): one instruction instead of the IEEE division's Newton step + slow path
 __device__ __forceinline__ float rcp_rn(float x) {
@@ -155,7 +169,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 __device__ __forceinline__ bool link_is_leaf(int32_t link) { return link < 0 && link != kLinkDone && link != kLinkPop; }
 
 #ifndef RT_EXT_MINB
-#define RT_EXT_MINB 0  // minimum resident CTAs per SM asked of the compiler (0: let it choose)
+#define RT_EXT_MINB 8  // minimum resident CTAs per SM asked of the compiler (0: let it choose); 8 = 64 registers, no spills
 #endif
 #if RT_EXT_MINB
 __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB) k_extend(
@@ -194,24 +208,34 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
     // scene BVH for the closest hit.  Both run in the same warp-synchronous loops, so the light-pdf traversals get
     // this kernel's lane occupancy and refill instead of k_shade's (7 of 32 lanes, 57 % of its instructions).
     bool lmode = false;
+#if RT_EXT_INLINE_LMODE
+    bool leaf_l = false;  // the postponed leaf belongs to the light BVH
+    const int32_t scene_root = RT_ROOT_OF(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT_OF(bvh);
+#endif
     float lsum = 0.0f;
 #if RT_EXT_WIDE4
     typedef QNode4 NodeT;
-#define RT_NODES(b) (b).qnodes4
-#define RT_ROOT(b) (b).root4
 #else
     typedef QNode NodeT;
-#define RT_NODES(b) (b).qnodes
-#define RT_ROOT(b) (b).root
 #endif
     const NodeT *node_base = RT_NODES(bvh);
+#if !RT_EXT_INLINE_LMODE
     const DTri *tri_base = bvh.tris;
+#endif
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes ---------------------------------------------------
         bool idle = link == kLinkDone && leaf == 0;
+#if RT_EXT_INLINE_LMODE
+        if (idle && ray != kNoRay) {  // bit 31 of `ray`: pending, its light pdf is wanted (0 without a light BVH)
+            const uint32_t r = ray & 0x7FFFFFFFu;
+            if (ray >> 31) q.lpdf[r] = lsum * inv_n_lights;
+            q.hit[r] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
+            ray = kNoRay;
+        }
+#else
         if (idle && ray != kNoRay) {
             if (lmode) {  // light pdf done: now the closest hit of the same ray
                 q.lpdf[ray] = lsum * inv_n_lights;
@@ -226,6 +250,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 ray = kNoRay;
             }
         }
+#endif
         const uint32_t m_idle = __ballot_sync(FULL, idle);
         if (m_idle) {
             if (pool_next == pool_end && !exhausted) {  // one atomicAdd per kRayBlock rays
@@ -258,6 +283,11 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 top = s_stack + threadIdx.x;
                 lmode = (__float_as_uint(d4.w) >> 31) != 0u && RT_ROOT(lbvh) != RT_LINK_NONE;
                 lsum = 0.0f;
+#if RT_EXT_INLINE_LMODE
+                ray |= __float_as_uint(d4.w) & 0x80000000u;
+                node_base = lmode ? RT_NODES(lbvh) : RT_NODES(bvh);
+                link = lmode ? RT_ROOT(lbvh) : scene_root;  // a leaf root is postponed below
+#else
                 if (lmode) {
                     node_base = RT_NODES(lbvh);
                     tri_base = lbvh.tris;
@@ -268,6 +298,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                     tri_base = bvh.tris;
                     link = RT_ROOT(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT(bvh);  // a leaf root is postponed below
                 }
+#endif
             }
             pool_next += take;
             if (avail == 0 && m_idle == FULL) break;  // queue drained and nothing in flight
@@ -287,6 +318,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             }
 #pragma unroll
             for (int step = 0; step < kStepsPerVote; ++step) {
+                auto node_step = [&]() {
                 // (4) at most one node step
                 if (link >= 0) {
                     auto push = [&](int32_t l, float t) {
@@ -350,6 +382,8 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                     link = (nt.hl || nt.hr) ? (right_first ? lr : ll) : kLinkPop;
 #endif
                 }
+                };
+                auto pop_step = [&]() {
                 // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
                 //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)
                 {
@@ -369,13 +403,35 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                             t = e.y;
                         }
                     }
+#if RT_EXT_INLINE_LMODE
+                    if (need && !has && lmode) {  // light BVH exhausted: on into the scene BVH (best_t is still +inf)
+                        lmode = false;
+                        node_base = RT_NODES(bvh);
+                        l = scene_root;
+                    }
+#endif
                     if (need) link = t < best_t ? l : kLinkPop;
                 }
+                };
+                auto postpone_step = [&]() {
                 // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
                 if (leaf == 0 && link_is_leaf(link)) {
                     leaf = link;
+#if RT_EXT_INLINE_LMODE
+                    leaf_l = lmode;
+#endif
                     link = kLinkPop;
                 }
+                };
+#if RT_EXT_STEP_ORDER == 0
+                node_step(); pop_step(); postpone_step();
+#elif RT_EXT_STEP_ORDER == 1
+                pop_step(); node_step(); postpone_step();
+#elif RT_EXT_STEP_ORDER == 2
+                pop_step(); node_step(); postpone_step(); pop_step();
+#else
+                pop_step(); postpone_step(); node_step(); pop_step(); postpone_step();
+#endif
             }
         }
 
@@ -385,7 +441,13 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             bool more = leaf != 0;
             while (__any_sync(FULL, more)) {
                 if (more) {
+#if RT_EXT_INLINE_LMODE
+                    const bool lt = leaf_l;
+                    const char *p = reinterpret_cast<const char *>((lt ? lbvh.tris : bvh.tris) + k);
+#else
+                    const bool lt = lmode;
                     const char *p = reinterpret_cast<const char *>(tri_base + k);
+#endif
                     const f8 ta = ld8(p);
                     const f4 t2 = ld4(p + 32);
                     const f4 t0 = f4{ta.a, ta.b, ta.c, ta.d}, t1 = f4{ta.e, ta.f, ta.g, ta.h};
@@ -398,7 +460,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                     const float inv = rcp_rn(-dot(d, n));
                     const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
                     if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < best_t) {
-                        if (lmode) {  // every hit counts, occluded or not, both faces (raytracer.h:79-84,255-261)
+                        if (lt) {  // every hit counts, occluded or not, both faces (raytracer.h:79-84,255-261)
                             const f4 le = ld4(light_extra + k);
                             const f3 xy = d * t;  // y - x
                             const float d2 = len2(xy);

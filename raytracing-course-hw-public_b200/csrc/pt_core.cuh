@@ -547,7 +547,12 @@ RT_HD float light_pdf(const DScene &s, f3 x, f3 dir) {
 // Texture::sample: repeat wrap, texel = (int)(u*W) without half-texel offset, bilinear with wrapped
 // neighbours, per-texel gamma BEFORE interpolation (LUT == powf(k/255, 2.2f)), alpha untouched;
 // 1-texel textures are returned raw (geometry.h:548-550).
-RT_HD f4 tex_sample(const DScene &s, const float *lut, int32_t tex, float u, float v, bool gamma) {
+#if defined(__CUDACC__) && defined(RT_TEX_NOINLINE)
+__host__ __device__ __noinline__
+#else
+RT_HD
+#endif
+f4 tex_sample(const DScene &s, const float *lut, int32_t tex, float u, float v, bool gamma) {
     const f4 ti = ld4(s.textures + tex);
     const uint32_t off = f2u(ti.x), w = f2u(ti.y), h = f2u(ti.z);
     const float k255 = 1.0f / 255.0f;
