@@ -141,8 +141,14 @@ constexpr int kMinSearching = RT_EXT_MIN_SEARCH;
 #define RT_EXT_STEPS_PER_VOTE 3  // 1 / 2 / 3 / 4 -> 103.4 / 100.4 / 99.3 / 100.4 ms of k_extend per 128 spp
 #endif
 constexpr int kStepsPerVote = RT_EXT_STEPS_PER_VOTE;
+#ifndef RT_EXT_PREFETCH_POOL
+#define RT_EXT_PREFETCH_POOL 0  // 1 / 2: prefetch a freshly taken block of ray records into L2 / L1
+#endif
+#ifndef RT_EXT_LEAF_PAIR
+#define RT_EXT_LEAF_PAIR 1  // 1: the leaf phase intersects two triangles per iteration
+#endif
 #ifndef RT_EXT_STEP_ORDER
-#define RT_EXT_STEP_ORDER 0  // 0: node, pop, postpone   1: pop, node, postpone   2: pop, node, postpone, pop   3: pop, postpone, node, pop, postpone
+#define RT_EXT_STEP_ORDER 1  // 0: node, pop, postpone   1: pop, node, postpone   2: pop, node, postpone, pop   3: pop, postpone, node, pop, postpone
 #endif
 #ifndef RT_EXT_INLINE_LMODE
 #define RT_EXT_INLINE_LMODE 1  // 1: a lane whose light-pdf traversal ends goes on into the scene BVH in the same step
@@ -262,6 +268,17 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 } else {
                     pool_next = base;
                     pool_end = base + kRayBlock < count ? base + kRayBlock : count;
+#if RT_EXT_PREFETCH_POOL
+                    {  // the block's 2 x 2 KB of ray records: one 128 B line per lane, on their way while the warp traverses
+                        const char *line = lane < 16 ? reinterpret_cast<const char *>(qo + base) + lane * 128
+                                                     : reinterpret_cast<const char *>(qd + base) + (lane - 16) * 128;
+#if RT_EXT_PREFETCH_POOL == 1
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+#else
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
+#endif
+                    }
+#endif
                 }
             }
             const uint32_t avail = pool_end - pool_next;
@@ -448,33 +465,46 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                     const bool lt = lmode;
                     const char *p = reinterpret_cast<const char *>(tri_base + k);
 #endif
-                    const f8 ta = ld8(p);
-                    const f4 t2 = ld4(p + 32);
-                    const f4 t0 = f4{ta.a, ta.b, ta.c, ta.d}, t1 = f4{ta.e, ta.f, ta.g, ta.h};
                     // intersect_ray_triangle, bvh.h:36-65 (same expression as tri_test() in pt_core.cuh with
                     // a correctly rounded reciprocal instead of the division)
-                    const f3 e1 = mk3(t1.x, t1.y, t1.z), e2 = mk3(t2.x, t2.y, t2.z);
-                    const f3 n = cross(e1, e2);
-                    const f3 y = o - mk3(t0.x, t0.y, t0.z);
-                    const f3 r = cross(d, y);
-                    const float inv = rcp_rn(-dot(d, n));
-                    const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
-                    if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < best_t) {
-                        if (lt) {  // every hit counts, occluded or not, both faces (raytracer.h:79-84,255-261)
-                            const f4 le = ld4(light_extra + k);
-                            const f3 xy = d * t;  // y - x
-                            const float d2 = len2(xy);
-                            const f3 w = xy * rsqrtf(d2);
-                            lsum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);
-                        } else {
-                            best_t = t;
-                            best_b = beta;
-                            best_c = gamma;
-                            best_tri = static_cast<int32_t>(k);
+                    auto tri = [&](const f8 &ta, const f4 &t2, uint32_t kk) {
+                        const f3 e1 = mk3(ta.e, ta.f, ta.g), e2 = mk3(t2.x, t2.y, t2.z);
+                        const f3 n = cross(e1, e2);
+                        const f3 y = o - mk3(ta.a, ta.b, ta.c);
+                        const f3 r = cross(d, y);
+                        const float inv = rcp_rn(-dot(d, n));
+                        const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
+                        if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < best_t) {
+                            if (lt) {  // every hit counts, occluded or not, both faces (raytracer.h:79-84,255-261)
+                                const f4 le = ld4(light_extra + kk);
+                                const f3 xy = d * t;  // y - x
+                                const float d2 = len2(xy);
+                                const f3 w = xy * rsqrtf(d2);
+                                lsum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);
+                            } else {
+                                best_t = t;
+                                best_b = beta;
+                                best_c = gamma;
+                                best_tri = static_cast<int32_t>(kk);
+                            }
                         }
-                    }
-                    more = !(f2u(t0.w) & RT_LAST_BIT);
+                        return (f2u(ta.d) & RT_LAST_BIT) != 0u;
+                    };
+#if RT_EXT_LEAF_PAIR
+                    // two triangles per iteration (the second one speculatively loaded: the array ends with a null
+                    // triangle): the scene's leaves mostly hold a quad, and the load latency is paid once per leaf
+                    const f8 ta = ld8(p), tb = ld8(p + 64);
+                    const f4 ta2 = ld4(p + 32), tb2 = ld4(p + 96);
+                    bool last = tri(ta, ta2, k);
+                    if (!last) last = tri(tb, tb2, k + 1);
+                    more = !last;
+                    k += 2;
+#else
+                    const f8 ta = ld8(p);
+                    const f4 t2 = ld4(p + 32);
+                    more = !tri(ta, t2, k);
                     ++k;
+#endif
                 }
             }
             leaf = 0;  // a lane that waited with a second leaf postpones it in step (2) of the next inner phase

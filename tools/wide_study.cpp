@@ -1,0 +1,378 @@
+// wide_study.cpp — host-side experiment (not part of the product, not part of the tests): how many node visits
+// do different wide-BVH traversal schemes need on the bench scene's path-traced ray distribution?
+//   A  4-wide, children sorted by entry distance, (link, t) stack with distance culling at pop  (what k_extend does)
+//   B  N-wide (4 or 8), octant-ordered slots, (node, hit-mask) stack without distances (Ylitie et al. 2017 style):
+//      a stale entry is only culled when its own children are tested against the shrunken best_t
+// Built by tools/wide_study.py into build/; prints counts per ray.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "pt_core.cuh"
+#include "repack.h"
+#include "rt_gpu.h"
+
+using namespace rt;
+
+namespace {
+struct WChild {
+    float lo[3], hi[3];
+    int32_t link;  // >= 0 wide node, < 0 leaf (~first tri), RT_LINK_NONE empty
+};
+struct WNode {
+    WChild ch[8];
+    int n;
+    int ax0, ax1;  // 4-wide: the two axes the slot bits refer to
+};
+struct Item {
+    int32_t link;
+    float lo[3], hi[3];
+};
+float area(const Item &c) {
+    const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+void kids(const DNode &n, Item out[2]) {
+    out[0] = Item{n.left, {n.lminx, n.lminy, n.lminz}, {n.lmaxx, n.lmaxy, n.lmaxz}};
+    out[1] = Item{n.right, {n.rminx, n.rminy, n.rminz}, {n.rmaxx, n.rmaxy, n.rmaxz}};
+}
+int32_t collapse(const std::vector<DNode> &nodes, int32_t link, int width, std::vector<WNode> &out) {
+    if (link < 0) return link;
+    Item it[8];
+    int n = 2;
+    kids(nodes[link], it);
+    while (n < width) {
+        int best = -1;
+        float ba = -1;
+        for (int i = 0; i < n; ++i)
+            if (it[i].link >= 0 && area(it[i]) > ba) ba = area(it[i]), best = i;
+        if (best < 0) break;
+        Item two[2];
+        kids(nodes[it[best].link], two);
+        it[best] = two[0];
+        it[n++] = two[1];
+    }
+    // slot assignment: greedy on dot(child centre - node centre, slot direction); slot s bit k set = positive side
+    float c[3] = {0, 0, 0}, lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = it[0].lo[k];
+        hi[k] = it[0].hi[k];
+        for (int i = 1; i < n; ++i) lo[k] = std::min(lo[k], it[i].lo[k]), hi[k] = std::max(hi[k], it[i].hi[k]);
+        c[k] = 0.5f * (lo[k] + hi[k]);
+    }
+    const int slots = width;
+    // 4 slots: the two axes along which the child centres spread most
+    int ax0 = 0, ax1 = 1;
+    {
+        float spread[3];
+        for (int k = 0; k < 3; ++k) {
+            float mn = 1e30f, mx = -1e30f;
+            for (int i = 0; i < n; ++i) {
+                const float cc = 0.5f * (it[i].lo[k] + it[i].hi[k]);
+                mn = std::min(mn, cc), mx = std::max(mx, cc);
+            }
+            spread[k] = mx - mn;
+        }
+        int order[3] = {0, 1, 2};
+        std::sort(order, order + 3, [&](int a, int b) { return spread[a] > spread[b]; });
+        ax0 = order[0];
+        ax1 = order[1];
+    }
+    int slot_of[8];
+    bool used[8] = {false}, done[8] = {false};
+    for (int round = 0; round < n; ++round) {
+        float bestv = -1e30f;
+        int bi = -1, bs = -1;
+        for (int i = 0; i < n; ++i) {
+            if (done[i]) continue;
+            for (int s = 0; s < slots; ++s) {
+                if (used[s]) continue;
+                float v = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const float cc = 0.5f * (it[i].lo[k] + it[i].hi[k]) - c[k];
+                    int bit;
+                    if (slots == 8) bit = (s >> k) & 1;
+                    else if (k == ax0) bit = s & 1;
+                    else if (k == ax1) bit = (s >> 1) & 1;
+                    else continue;
+                    v += bit ? cc : -cc;
+                }
+                if (v > bestv) bestv = v, bi = i, bs = s;
+            }
+        }
+        done[bi] = true;
+        used[bs] = true;
+        slot_of[bi] = bs;
+    }
+    const int32_t idx = (int32_t)out.size();
+    out.emplace_back();
+    WNode w;
+    w.n = slots;
+    w.ax0 = ax0;
+    w.ax1 = ax1;
+    for (int s = 0; s < 8; ++s) w.ch[s].link = RT_LINK_NONE;
+    for (int i = 0; i < n; ++i) {
+        WChild &cdst = w.ch[slot_of[i]];
+        std::memcpy(cdst.lo, it[i].lo, 12);
+        std::memcpy(cdst.hi, it[i].hi, 12);
+        cdst.link = it[i].link;
+    }
+    out[idx] = w;
+    for (int s = 0; s < slots; ++s)
+        if (out[idx].ch[s].link != RT_LINK_NONE && out[idx].ch[s].link >= 0) {
+            const int32_t l = collapse(nodes, out[idx].ch[s].link, width, out);
+            out[idx].ch[s].link = l;
+        }
+    return idx;
+}
+
+struct Cnt {
+    uint64_t rays = 0, nodes = 0, tris = 0, pops = 0, culled = 0, leaves = 0, pushes = 0;
+};
+
+bool tri_hit(const DBvh &bvh, uint32_t k, f3 o, f3 d, float eps, Hit &best) {
+    const char *p = reinterpret_cast<const char *>(bvh.tris + k);
+    const f4 t0 = ld4(p), t1 = ld4(p + 16), t2 = ld4(p + 32);
+    float t, b, c;
+    if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, eps, t, b, c) && t < best.t) {
+        best.t = t;
+        best.b = b;
+        best.c = c;
+        best.tri = (int32_t)k;
+    }
+    return (f2u(t0.w) & RT_LAST_BIT) != 0;
+}
+
+// scheme B
+Hit trav_oct(const std::vector<WNode> &W, int32_t root, int width, const DBvh &bvh, f3 o, f3 d, float eps, Cnt &c, bool by_dist) {
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0;
+    best.tri = -1;
+    ++c.rays;
+    const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float dd[3] = {d.x, d.y, d.z};
+    auto inv_of = [&](const WNode &n) {
+        if (width == 8) return (d.x < 0 ? 0 : 1) | (d.y < 0 ? 0 : 2) | (d.z < 0 ? 0 : 4);
+        return (dd[n.ax0] < 0 ? 0 : 1) | (dd[n.ax1] < 0 ? 0 : 2);
+    };
+    struct E {
+        int32_t node;
+        uint32_t mask;
+    };
+    E st[256];
+    int sp = 0;
+    if (root < 0) {
+        for (uint32_t k = (uint32_t)~root;; ++k) {
+            ++c.tris;
+            if (tri_hit(bvh, k, o, d, eps, best)) break;
+        }
+        return best;
+    }
+    int32_t cur = root;
+    for (;;) {
+        ++c.nodes;
+        const WNode &n = W[cur];
+        uint32_t mask = 0;
+        float dist[8];
+        for (int s = 0; s < width; ++s) {
+            const WChild &ch = n.ch[s];
+            if (ch.link == RT_LINK_NONE) continue;
+            const float t = slab(ch.lo[0], ch.lo[1], ch.lo[2], ch.hi[0], ch.hi[1], ch.hi[2], o, idir, eps);
+            if (t >= 0.0f && t < best.t) {
+                mask |= 1u << s;
+                dist[s] = t;
+            }
+        }
+        // leaves first (Ylitie: triangles of the node are intersected before descending), in priority order
+        E e{cur, mask};
+        for (;;) {
+            // next child by priority
+            int pick = -1;
+            if (!by_dist) {
+                int bestp = -1;
+                for (int s = 0; s < width; ++s)
+                    if (e.mask >> s & 1) {
+                        const int pr = (s ^ inv_of(W[e.node])) & (width - 1);
+                        if (pr > bestp) bestp = pr, pick = s;
+                    }
+            } else {
+                float bd = INFINITY;
+                for (int s = 0; s < width; ++s)
+                    if ((e.mask >> s & 1) && dist[s] < bd) bd = dist[s], pick = s;
+            }
+            if (pick < 0) break;
+            e.mask &= ~(1u << pick);
+            const int32_t l = W[e.node].ch[pick].link;
+            if (l < 0) {
+                ++c.leaves;
+                for (uint32_t k = (uint32_t)~l;; ++k) {
+                    ++c.tris;
+                    if (tri_hit(bvh, k, o, d, eps, best)) break;
+                }
+                continue;
+            }
+            if (e.mask) {
+                st[sp++] = e;
+                ++c.pushes;
+            }
+            cur = l;
+            goto next_node;
+        }
+        // pop
+        for (;;) {
+            if (sp == 0) return best;
+            E &t = st[sp - 1];
+            ++c.pops;
+            int pick = -1, bestp = -1;
+            for (int s = 0; s < width; ++s)
+                if (t.mask >> s & 1) {
+                    const int pr = (s ^ inv_of(W[t.node])) & (width - 1);
+                    if (pr > bestp) bestp = pr, pick = s;
+                }
+            t.mask &= ~(1u << pick);
+            const int32_t node = t.node;
+            if (!t.mask) --sp;
+            const int32_t l = W[node].ch[pick].link;
+            if (l < 0) {
+                ++c.leaves;
+                for (uint32_t k = (uint32_t)~l;; ++k) {
+                    ++c.tris;
+                    if (tri_hit(bvh, k, o, d, eps, best)) break;
+                }
+                continue;
+            }
+            cur = l;
+            break;
+        }
+    next_node:;
+    }
+}
+
+// scheme A on the same wide nodes: sorted by distance, (link, t) stack, cull at pop
+Hit trav_sorted(const std::vector<WNode> &W, int32_t root, int width, const DBvh &bvh, f3 o, f3 d, float eps, Cnt &c) {
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0;
+    best.tri = -1;
+    ++c.rays;
+    const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int32_t sl[512];
+    float stt[512];
+    int sp = 0;
+    int32_t link = root;
+    for (;;) {
+        if (link >= 0) {
+            ++c.nodes;
+            const WNode &n = W[link];
+            float dist[8];
+            int32_t ls[8];
+            int m = 0;
+            for (int s = 0; s < width; ++s) {
+                const WChild &ch = n.ch[s];
+                if (ch.link == RT_LINK_NONE) continue;
+                const float t = slab(ch.lo[0], ch.lo[1], ch.lo[2], ch.hi[0], ch.hi[1], ch.hi[2], o, idir, eps);
+                if (t >= 0.0f && t < best.t) dist[m] = t, ls[m++] = ch.link;
+            }
+            for (int i = 1; i < m; ++i)
+                for (int j = i; j > 0 && dist[j] < dist[j - 1]; --j) std::swap(dist[j], dist[j - 1]), std::swap(ls[j], ls[j - 1]);
+            for (int i = m - 1; i >= 1; --i) sl[sp] = ls[i], stt[sp++] = dist[i], ++c.pushes;
+            if (m > 0) {
+                link = ls[0];
+                continue;
+            }
+        } else {
+            ++c.leaves;
+            for (uint32_t k = (uint32_t)~link;; ++k) {
+                ++c.tris;
+                if (tri_hit(bvh, k, o, d, eps, best)) break;
+            }
+        }
+        for (;;) {
+            if (sp == 0) return best;
+            --sp;
+            ++c.pops;
+            if (stt[sp] < best.t) {
+                link = sl[sp];
+                break;
+            }
+            ++c.culled;
+        }
+    }
+}
+
+void report(const char *name, const Cnt &c) {
+    const double r = (double)c.rays;
+    std::printf("%-34s nodes/ray %6.2f  leaves %5.2f  tris %5.2f  pushes %5.2f  pops %5.2f  culled pops %5.2f\n", name, c.nodes / r,
+                c.leaves / r, c.tris / r, c.pushes / r, c.pops / r, c.culled / r);
+}
+}  // namespace
+
+extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint32_t spp) {
+    PackedScene p;
+    if (int rc = pack_scene(*sc, p, true)) return rc;
+    DScene d;
+    fill_scene_constants(*sc, p, d);
+    d.scene.nodes = p.scene.nodes.data();
+    d.scene.qnodes = p.scene.qnodes.data();
+    d.scene.qnodes4 = p.scene.qnodes4.data();
+    d.light.qnodes4 = p.light.qnodes4.data();
+    d.light.qnodes = p.light.qnodes.data();
+    d.scene.tris = p.scene.tris.data();
+    d.light.nodes = p.light.nodes.data();
+    d.light.tris = p.light.tris.data();
+    d.light_sample = p.light_sample.data();
+    d.attrs = p.attrs.data();
+    d.tangents = p.tangents.empty() ? nullptr : p.tangents.data();
+    d.light_extra = p.light_extra.data();
+    d.materials = p.materials.data();
+    d.textures = p.textures.data();
+    d.texels = p.texels.data();
+    std::vector<WNode> W4, W8;
+    const int32_t r4 = collapse(p.scene.nodes, p.scene.root, 4, W4), r8 = collapse(p.scene.nodes, p.scene.root, 8, W8);
+    std::printf("binary inner nodes %zu, 4-wide %zu, 8-wide %zu\n", p.scene.nodes.size(), W4.size(), W8.size());
+    Camera c;
+    c.pos = mk3(d.cam_pos[0], d.cam_pos[1], d.cam_pos[2]);
+    c.right = mk3(d.cam_right[0], d.cam_right[1], d.cam_right[2]);
+    c.up = mk3(d.cam_up[0], d.cam_up[1], d.cam_up[2]);
+    c.fwd = mk3(d.cam_fwd[0], d.cam_fwd[1], d.cam_fwd[2]);
+    c.tan_half_x = tanf(d.fov_x / 2);
+    c.tan_half_y = tanf(atanf(tanf(d.fov_x / 2) * (float)h / (float)w));
+    c.inv_w2 = 2.0f / (float)w;
+    c.inv_h2 = 2.0f / (float)h;
+    Cnt a4, b4, b4d, a8, b8, b8d, q4;
+    uint64_t mism = 0;
+    for (uint32_t pix = 0; pix < w * h; ++pix)
+        for (uint32_t s = 0; s < spp; ++s) {
+            const RngKey key{pix, s, 7u, 0u};
+            const u4 j = rng_jitter(key);
+            f3 o = c.pos;
+            f3 dir = camera_dir(c, (float)(pix % w) + u01(j.x), (float)(pix / w) + u01(j.y));
+            f3 thr = mk3(1, 1, 1), rad = mk3(0, 0, 0);
+            for (uint32_t b = 0; b < d.ray_depth; ++b) {
+                uint32_t st = 0;
+                const Hit hit = closest_hit_q4(d.scene, o, dir, d.eps, &st);
+                q4.nodes += st;
+                ++q4.rays;
+                const Hit h1 = trav_sorted(W4, r4, 4, d.scene, o, dir, d.eps, a4);
+                const Hit h2 = trav_oct(W4, r4, 4, d.scene, o, dir, d.eps, b4, false);
+                trav_oct(W4, r4, 4, d.scene, o, dir, d.eps, b4d, true);
+                trav_sorted(W8, r8, 8, d.scene, o, dir, d.eps, a8);
+                const Hit h3 = trav_oct(W8, r8, 8, d.scene, o, dir, d.eps, b8, false);
+                trav_oct(W8, r8, 8, d.scene, o, dir, d.eps, b8d, true);
+                mism += (h1.tri != hit.tri) + (h2.tri != hit.tri) + (h3.tri != hit.tri);
+                uint32_t lr = 0;
+                if (!shade_bounce(d, p.gamma_lut, key, b, b + 1 == d.ray_depth, hit, o, dir, thr, rad, lr)) break;
+            }
+        }
+    std::printf("rays %llu, hit mismatches vs the quantised 4-wide traversal %llu\n", (unsigned long long)q4.rays, (unsigned long long)mism);
+    report("k_extend's 4-wide (quantised)", q4);
+    report("A4 sorted + distance stack", a4);
+    report("B4 octant order, mask stack", b4);
+    report("B4 distance order, mask stack", b4d);
+    report("A8 sorted + distance stack", a8);
+    report("B8 octant order, mask stack", b8);
+    report("B8 distance order, mask stack", b8d);
+    return 0;
+}
