@@ -141,9 +141,6 @@ constexpr int kMinSearching = RT_EXT_MIN_SEARCH;
 #define RT_EXT_STEPS_PER_VOTE 3  // 1 / 2 / 3 / 4 -> 103.4 / 100.4 / 99.3 / 100.4 ms of k_extend per 128 spp
 #endif
 constexpr int kStepsPerVote = RT_EXT_STEPS_PER_VOTE;
-#ifndef RT_EXT_PREFETCH_POOL
-#define RT_EXT_PREFETCH_POOL 0  // 1 / 2: prefetch a freshly taken block of ray records into L2 / L1
-#endif
 #ifndef RT_EXT_LEAF_PAIR
 #define RT_EXT_LEAF_PAIR 1  // 1: the leaf phase intersects two triangles per iteration
 #endif
@@ -268,17 +265,6 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 } else {
                     pool_next = base;
                     pool_end = base + kRayBlock < count ? base + kRayBlock : count;
-#if RT_EXT_PREFETCH_POOL
-                    {  // the block's 2 x 2 KB of ray records: one 128 B line per lane, on their way while the warp traverses
-                        const char *line = lane < 16 ? reinterpret_cast<const char *>(qo + base) + lane * 128
-                                                     : reinterpret_cast<const char *>(qd + base) + (lane - 16) * 128;
-#if RT_EXT_PREFETCH_POOL == 1
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-#else
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
-#endif
-                    }
-#endif
                 }
             }
             const uint32_t avail = pool_end - pool_next;
