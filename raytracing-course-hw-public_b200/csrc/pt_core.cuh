@@ -416,6 +416,122 @@ RT_HD Hit closest_hit_q4(const DBvh &bvh, f3 o, f3 d, float min_dst, uint32_t *s
     }
 }
 
+// ---- 8-wide quantised node (QNode8, rt_types.h): eight slab tests from one 96-byte record ----------------------------
+RT_HD uint32_t bfind32(uint32_t x) {  // index of the highest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+    return 31u - static_cast<uint32_t>(__clz(static_cast<int>(x)));
+#else
+    return 31u - static_cast<uint32_t>(__builtin_clz(x));
+#endif
+}
+RT_HD uint32_t popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return static_cast<uint32_t>(__popc(x));
+#else
+    return static_cast<uint32_t>(__builtin_popcount(x));
+#endif
+}
+// octinv: bit k set where the ray runs in the POSITIVE direction of axis k.  A child in slot s (bit k set = positive
+// side along axis k) is visited in the order of decreasing s ^ octinv: near side first along every axis.
+RT_HD uint32_t ray_octinv(f3 d) { return (d.x < 0.0f ? 0u : 1u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 4u); }
+// bit s of m -> bit s ^ octinv
+RT_HD uint32_t oct_permute(uint32_t m, uint32_t octinv) {
+    if (octinv & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+    if (octinv & 2u) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+    if (octinv & 4u) m = ((m & 0x0Fu) << 4) | ((m >> 4) & 0x0Fu);
+    return m;
+}
+struct Grid3 {
+    float ax, bx, ay, by, az, bz;
+};
+RT_HD Grid3 qgrid(uint32_t ox, uint32_t oy, uint32_t oz, f3 idir, f3 ood) {
+    Grid3 g;
+    g.ax = u2f((ox << 23) + 0x08000000u) * idir.x, g.bx = fmaf(u2f(ox), idir.x, -ood.x) - g.ax;
+    g.ay = u2f((oy << 23) + 0x08000000u) * idir.y, g.by = fmaf(u2f(oy), idir.y, -ood.y) - g.ay;
+    g.az = u2f((oz << 23) + 0x08000000u) * idir.z, g.bz = fmaf(u2f(oz), idir.z, -ood.z) - g.az;
+    return g;
+}
+// hit bits of the four children of one plane group (lo x/y/z, hi x/y/z words)
+RT_HD uint32_t q8_group_hits(uint32_t lox, uint32_t loy, uint32_t loz, uint32_t hix, uint32_t hiy, uint32_t hiz, const Grid3 &g, bool px,
+                             bool py, bool pz, uint32_t one, float eps, float best_t) {
+    const uint32_t nx = px ? lox : hix, fx = px ? hix : lox;
+    const uint32_t ny = py ? loy : hiy, fy = py ? hiy : loy;
+    const uint32_t nz = pz ? loz : hiz, fz = pz ? hiz : loz;
+    uint32_t m = 0;
+    m |= q4_entry<0>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 1u : 0u;
+    m |= q4_entry<1>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 2u : 0u;
+    m |= q4_entry<2>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 4u : 0u;
+    m |= q4_entry<3>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 8u : 0u;
+    return m;
+}
+// triangle position of the leaf child in slot s: tri_base + the counts (2 bits per slot) of the lower slots
+RT_HD uint32_t leaf8_offset(uint32_t counts, uint32_t s) {
+    const uint32_t below = counts & ((1u << (2u * s)) - 1u);
+    return popc32(below & 0x5555u) + 2u * popc32(below & 0xAAAAu);
+}
+
+// closest_hit() over the 8-wide nodes: the sequential statement of k_extend's 8-wide mode (group stack without
+// distances: an entry is culled when its own children are tested against the current best).  `steps` counts node steps.
+RT_HD Hit closest_hit_q8(const DBvh &bvh, f3 o, f3 d, float min_dst, uint32_t *steps) {
+    Hit best;
+    best.t = INFINITY;
+    best.b = best.c = 0.0f;
+    best.tri = -1;
+    if (bvh.n_nodes8 == 0) return best;
+    const f3 idir = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const bool px = !(idir.x < 0.0f), py = !(idir.y < 0.0f), pz = !(idir.z < 0.0f);
+    const uint32_t octinv = (px ? 1u : 0u) | (py ? 2u : 0u) | (pz ? 4u : 0u);
+    uint32_t sx[RT_STACK_SIZE], sy[RT_STACK_SIZE];
+    int sp = 0;
+    uint32_t gx = 0, gy = 0x80000000u;  // pseudo group: "child 0 of nothing" = the root
+    for (;;) {
+        if (gy >> 24) {
+            const uint32_t p = bfind32(gy);
+            const uint32_t slot = (p - 24u) ^ octinv;
+            gy &= ~(1u << p);
+            const uint32_t child = gx + popc32(gy & 0xFFu & ((1u << slot) - 1u));
+            if (gy >> 24) {
+                sx[sp] = gx;
+                sy[sp++] = gy;
+            }
+            if (steps) ++*steps;
+            const char *np = reinterpret_cast<const char *>(bvh.qnodes8 + child);
+            const f8 h = ld8(np), a = ld8(np + 32), b = ld8(np + 64);
+            const Grid3 g = qgrid(f2u(h.a), f2u(h.b), f2u(h.c), idir, ood);
+            const uint32_t hs = q8_group_hits(f2u(a.a), f2u(a.b), f2u(a.c), f2u(a.d), f2u(a.e), f2u(a.f), g, px, py, pz, qnode_one(), min_dst, best.t) |
+                                q8_group_hits(f2u(b.a), f2u(b.b), f2u(b.c), f2u(b.d), f2u(b.e), f2u(b.f), g, px, py, pz, qnode_one(), min_dst, best.t) << 4;
+            const uint32_t imask = f2u(h.d), counts = f2u(h.g);
+            uint32_t leaf = hs & ~imask;
+            while (leaf) {  // highest slot first, like the kernel's leaf phase
+                const uint32_t s = bfind32(leaf);
+                leaf &= ~(1u << s);
+                uint32_t k = f2u(h.f) + leaf8_offset(counts, s);
+                for (;;) {
+                    const char *tp = reinterpret_cast<const char *>(bvh.tris + k);
+                    const f4 t0 = ld4(tp), t1 = ld4(tp + 16), t2 = ld4(tp + 32);
+                    float t, bb, cc;
+                    if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), o, d, min_dst, t, bb, cc) && t < best.t) {
+                        best.t = t;
+                        best.b = bb;
+                        best.c = cc;
+                        best.tri = static_cast<int32_t>(k);
+                    }
+                    if (f2u(t0.w) & RT_LAST_BIT) break;
+                    ++k;
+                }
+            }
+            gx = f2u(h.e);
+            gy = (oct_permute(hs & imask, octinv) << 24) | (imask & 0xFFu);
+            if (gy >> 24) continue;
+        }
+        if (sp == 0) return best;
+        --sp;
+        gx = sx[sp];
+        gy = sy[sp];
+    }
+}
+
 struct TravCounters {
     uint32_t nodes, tris;
 };
@@ -489,8 +605,68 @@ RT_HD Hit closest_hit(const DBvh &bvh, f3 o, f3 d, float min_dst) {
 // bvh_mix_dist::pdf, raytracer.h:363-375: ALL hits along (x, dir) with t >= eps, occluded or not,
 // both faces; each contributes |y - x|^2 / (|dir . n_y| * area) (raytracer.h:79-84,255-261);
 // the sum is divided by the number of lights.  BVH::foreach_intersection, bvh.h:237-260.
+// the same sum over the 8-wide light BVH (every node whose box the ray meets, every triangle hit)
+RT_HD float light_pdf_q8(const DScene &s, f3 x, f3 dir) {
+    const DBvh &bvh = s.light;
+    const f3 idir = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    const f3 ood = mk3(x.x * idir.x, x.y * idir.y, x.z * idir.z);
+    const bool px = !(idir.x < 0.0f), py = !(idir.y < 0.0f), pz = !(idir.z < 0.0f);
+    uint32_t sx[RT_STACK_SIZE], sy[RT_STACK_SIZE];
+    int sp = 0;
+    uint32_t gx = 0, gy = 0x80000000u;
+    float sum = 0.0f;
+    for (;;) {
+        if (gy >> 24) {
+            const uint32_t p = bfind32(gy);
+            const uint32_t slot = p - 24u;  // no ordering needed: all hits count
+            gy &= ~(1u << p);
+            const uint32_t child = gx + popc32(gy & 0xFFu & ((1u << slot) - 1u));
+            if (gy >> 24) {
+                sx[sp] = gx;
+                sy[sp++] = gy;
+            }
+            const char *np = reinterpret_cast<const char *>(bvh.qnodes8 + child);
+            const f8 h = ld8(np), a = ld8(np + 32), b = ld8(np + 64);
+            const Grid3 g = qgrid(f2u(h.a), f2u(h.b), f2u(h.c), idir, ood);
+            const uint32_t hs = q8_group_hits(f2u(a.a), f2u(a.b), f2u(a.c), f2u(a.d), f2u(a.e), f2u(a.f), g, px, py, pz, qnode_one(), s.eps, INFINITY) |
+                                q8_group_hits(f2u(b.a), f2u(b.b), f2u(b.c), f2u(b.d), f2u(b.e), f2u(b.f), g, px, py, pz, qnode_one(), s.eps, INFINITY) << 4;
+            const uint32_t imask = f2u(h.d), counts = f2u(h.g);
+            uint32_t leaf = hs & ~imask;
+            while (leaf) {
+                const uint32_t sl = bfind32(leaf);
+                leaf &= ~(1u << sl);
+                uint32_t k = f2u(h.f) + leaf8_offset(counts, sl);
+                for (;;) {
+                    const char *tp = reinterpret_cast<const char *>(bvh.tris + k);
+                    const f4 t0 = ld4(tp), t1 = ld4(tp + 16), t2 = ld4(tp + 32);
+                    float t, bb, cc;
+                    if (tri_test(mk3(t0.x, t0.y, t0.z), mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z), x, dir, s.eps, t, bb, cc)) {
+                        const f4 le = ld4(s.light_extra + k);
+                        const f3 y = x + dir * t;
+                        const f3 xy = y - x;
+                        const float d2 = len2(xy);
+                        const f3 w = xy * (1.0f / sqrtf(d2));
+                        sum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);
+                    }
+                    if (f2u(t0.w) & RT_LAST_BIT) break;
+                    ++k;
+                }
+            }
+            gx = f2u(h.e);
+            gy = ((hs & imask) << 24) | (imask & 0xFFu);
+            if (gy >> 24) continue;
+        }
+        if (sp == 0) break;
+        --sp;
+        gx = sx[sp];
+        gy = sy[sp];
+    }
+    return sum / static_cast<float>(s.n_lights);
+}
+
 RT_HD float light_pdf(const DScene &s, f3 x, f3 dir) {
     const DBvh &bvh = s.light;
+    if (bvh.n_nodes8 != 0) return light_pdf_q8(s, x, dir);
     if (bvh.root == RT_LINK_NONE) return 0.0f;
     const f3 idir = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     int32_t stack_link[RT_STACK_SIZE];

@@ -23,6 +23,8 @@ struct PackedBvh {
     std::vector<QNode> qnodes;    // quantised copy of `nodes` (same indices), see quantize_nodes()
     std::vector<QNode4> qnodes4;  // 4-wide collapse of the same tree (own indices), see collapse4()
     int32_t root4 = RT_LINK_NONE;
+    std::vector<QNode8> qnodes8;  // 8-wide collapse (RT_PACK_Q8 only: `tris` / `order` are then in ITS triangle order and
+                                  // the 2- and 4-wide arrays are not produced); node 0 is the root
     std::vector<DTri> tris;       // BVH object order
     std::vector<uint32_t> order;  // BVH position -> scene.objects index
     int32_t root = RT_LINK_NONE;
@@ -286,16 +288,224 @@ inline int quantize_nodes4(const std::vector<Node4Boxes> &boxes, std::vector<QNo
     return rc;
 }
 
+// ---- 8-wide collapse (QNode8) ---------------------------------------------------------------------------------
+constexpr uint32_t kLeaf8 = 3;  // triangles per leaf child (2 count bits per slot)
+struct Item8 {
+    int32_t link;     // >= 0: inner node of the binary tree; < 0: the triangle range [tb, te) (BVH-order positions)
+    uint32_t tb, te;
+    float lo[3], hi[3];
+    bool openable() const { return link >= 0 || te - tb > kLeaf8; }
+};
+struct Node8Boxes {
+    float lo[8][3], hi[8][3];
+    uint8_t present;
+};
+inline float box_area(const Item8 &c) {
+    const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+struct Collapse8 {
+    const std::vector<DNode> &nodes;
+    const std::vector<DTri> &tris;  // BVH order, RT_LAST_BIT marks the ends of the binary leaves
+    std::vector<QNode8> &out;
+    std::vector<Node8Boxes> &boxes;
+    std::vector<uint32_t> &perm;  // new triangle position -> old (BVH-order) position
+    std::vector<uint32_t> &last;  // new positions that end a leaf child
+
+    Item8 range_item(uint32_t tb, uint32_t te) const {
+        Item8 it;
+        it.link = -1;
+        it.tb = tb;
+        it.te = te;
+        const float inf = std::numeric_limits<float>::infinity();
+        for (int k = 0; k < 3; ++k) it.lo[k] = inf, it.hi[k] = -inf;
+        for (uint32_t i = tb; i < te; ++i) {
+            const DTri &t = tris[i];
+            const float a[3] = {t.ax, t.ay, t.az}, e1[3] = {t.e1x, t.e1y, t.e1z}, e2[3] = {t.e2x, t.e2y, t.e2z};
+            for (int k = 0; k < 3; ++k) {
+                // the vertices as the builders saw them: b = a + (b - a) may differ from b in the last bit, so the box
+                // takes both roundings into account by a one-ulp widening
+                const float v1 = a[k] + e1[k], v2 = a[k] + e2[k];
+                const float mn = std::min(a[k], std::min(v1, v2)), mx = std::max(a[k], std::max(v1, v2));
+                it.lo[k] = std::min(it.lo[k], std::nextafterf(mn, -inf));
+                it.hi[k] = std::max(it.hi[k], std::nextafterf(mx, inf));
+            }
+        }
+        return it;
+    }
+    Item8 link_item(int32_t link, const float *lo, const float *hi) const {
+        Item8 it;
+        if (link >= 0) {
+            it.link = link;
+            it.tb = it.te = 0;
+        } else {  // binary leaf: its triangle run
+            it.link = -1;
+            it.tb = static_cast<uint32_t>(~link);
+            it.te = it.tb;
+            while (!(tris[it.te].id_last & RT_LAST_BIT)) ++it.te;
+            ++it.te;
+        }
+        std::memcpy(it.lo, lo, 12);
+        std::memcpy(it.hi, hi, 12);
+        return it;
+    }
+    void open(const Item8 &it, Item8 two[2]) const {
+        if (it.link >= 0) {
+            const DNode &n = nodes[it.link];
+            const float llo[3] = {n.lminx, n.lminy, n.lminz}, lhi[3] = {n.lmaxx, n.lmaxy, n.lmaxz};
+            const float rlo[3] = {n.rminx, n.rminy, n.rminz}, rhi[3] = {n.rmaxx, n.rmaxy, n.rmaxz};
+            two[0] = link_item(n.left, llo, lhi);
+            two[1] = link_item(n.right, rlo, rhi);
+        } else {  // a leaf of more than kLeaf8 triangles: halves (the run keeps its order)
+            const uint32_t mid = it.tb + (it.te - it.tb + 1) / 2;
+            two[0] = range_item(it.tb, mid);
+            two[1] = range_item(mid, it.te);
+        }
+    }
+    // builds wide node `idx` (already allocated) from `self`
+    void build(const Item8 &self, uint32_t idx) {
+        Item8 it[8];
+        int n;
+        if (self.openable()) {
+            open(self, it);
+            n = 2;
+        } else {
+            it[0] = self;
+            n = 1;
+        }
+        while (n < 8) {  // open the child with the largest box until eight children or nothing left to open
+            int best = -1;
+            float best_area = -1.0f;
+            for (int i = 0; i < n; ++i)
+                if (it[i].openable() && box_area(it[i]) > best_area) {
+                    best_area = box_area(it[i]);
+                    best = i;
+                }
+            if (best < 0) break;
+            Item8 two[2];
+            open(it[best], two);
+            it[best] = two[0];
+            it[n++] = two[1];
+        }
+        // slots by octant: greedily the (child, slot) pair with the largest dot(child centre - node centre, slot direction)
+        float c[3];
+        for (int k = 0; k < 3; ++k) {
+            float lo = it[0].lo[k], hi = it[0].hi[k];
+            for (int i = 1; i < n; ++i) lo = std::min(lo, it[i].lo[k]), hi = std::max(hi, it[i].hi[k]);
+            c[k] = 0.5f * (lo + hi);
+        }
+        int slot_of[8];
+        bool used[8] = {false, false, false, false, false, false, false, false}, done[8] = {false, false, false, false, false, false, false, false};
+        for (int round = 0; round < n; ++round) {
+            float bestv = -std::numeric_limits<float>::infinity();
+            int bi = -1, bs = -1;
+            for (int i = 0; i < n; ++i) {
+                if (done[i]) continue;
+                for (int s = 0; s < 8; ++s) {
+                    if (used[s]) continue;
+                    float v = 0.0f;
+                    for (int k = 0; k < 3; ++k) {
+                        const float cc = 0.5f * (it[i].lo[k] + it[i].hi[k]) - c[k];
+                        v += ((s >> k) & 1) ? cc : -cc;
+                    }
+                    if (v > bestv || bi < 0) bestv = v, bi = i, bs = s;
+                }
+            }
+            done[bi] = true;
+            used[bs] = true;
+            slot_of[bi] = bs;
+        }
+        int item_in[8];
+        for (int s = 0; s < 8; ++s) item_in[s] = -1;
+        for (int i = 0; i < n; ++i) item_in[slot_of[i]] = i;
+        QNode8 q;
+        std::memset(&q, 0, sizeof q);
+        Node8Boxes nb;
+        std::memset(&nb, 0, sizeof nb);
+        q.child_base = static_cast<uint32_t>(out.size());
+        q.tri_base = static_cast<uint32_t>(perm.size());
+        uint32_t n_inner = 0;
+        for (int s = 0; s < 8; ++s) {
+            const int i = item_in[s];
+            if (i < 0) continue;
+            nb.present |= static_cast<uint8_t>(1u << s);
+            std::memcpy(nb.lo[s], it[i].lo, 12);
+            std::memcpy(nb.hi[s], it[i].hi, 12);
+            if (it[i].openable()) {
+                q.imask |= 1u << s;
+                ++n_inner;
+            } else {
+                q.counts |= (it[i].te - it[i].tb) << (2 * s);
+                for (uint32_t t = it[i].tb; t < it[i].te; ++t) perm.push_back(t);
+                last.push_back(static_cast<uint32_t>(perm.size() - 1));
+            }
+        }
+        out.resize(out.size() + n_inner);
+        boxes.resize(out.size());
+        out[idx] = q;
+        boxes[idx] = nb;
+        uint32_t rank = 0;
+        for (int s = 0; s < 8; ++s)
+            if (q.imask >> s & 1u) build(it[item_in[s]], q.child_base + rank++);
+    }
+};
+inline int quantize_nodes8(const std::vector<Node8Boxes> &boxes, std::vector<QNode8> &out) {
+    std::atomic<int> rc{RT_OK};
+    parallel_for(out.size(), [&](size_t b, size_t e) {
+        for (size_t k = b; k < e; ++k) {
+            const Node8Boxes &nb = boxes[k];
+            QNode8 &q = out[k];
+            for (int a = 0; a < 3; ++a) {
+                float lo[8], hi[8];
+                uint8_t ql[8], qh[8], fl[8], fh[8];
+                int m = 0;
+                for (int s = 0; s < 8; ++s)
+                    if (nb.present >> s & 1) {
+                        lo[m] = nb.lo[s][a];
+                        hi[m] = nb.hi[s][a];
+                        ++m;
+                    }
+                if (!quantize_axis_n(lo, hi, m, q.org[a], ql, qh)) rc = RT_ERR_BAD_SCENE;
+                m = 0;
+                for (int s = 0; s < 8; ++s) {
+                    if (nb.present >> s & 1) {
+                        fl[s] = ql[m];
+                        fh[s] = qh[m];
+                        ++m;
+                    } else {  // empty slot: inverted box, never hit
+                        fl[s] = 255;
+                        fh[s] = 0;
+                    }
+                }
+                auto word = [](const uint8_t *p) {
+                    return static_cast<uint32_t>(p[0]) | static_cast<uint32_t>(p[1]) << 8 | static_cast<uint32_t>(p[2]) << 16 |
+                           static_cast<uint32_t>(p[3]) << 24;
+                };
+                q.g0[a] = word(fl);
+                q.g0[3 + a] = word(fh);
+                q.g1[a] = word(fl + 4);
+                q.g1[3 + a] = word(fh + 4);
+            }
+        }
+    });
+    return rc;
+}
+
 }  // namespace detail
 
 // `formats`: which quantised node arrays to produce (the device build needs one, the host checks both)
-enum { RT_PACK_Q2 = 1, RT_PACK_Q4 = 2, RT_PACK_ALL = 3 };
+// RT_PACK_Q8 re-orders the triangles, so it excludes the other two
+enum { RT_PACK_Q2 = 1, RT_PACK_Q4 = 2, RT_PACK_ALL = 3, RT_PACK_Q8 = 4 };
 inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &out, int formats = RT_PACK_ALL) {
     out.nodes.clear();
     out.tris.assign(src.n_objects, DTri());
     out.order.assign(src.objects, src.objects + src.n_objects);
     out.root = RT_LINK_NONE;
+    out.root4 = RT_LINK_NONE;
     out.max_depth = 0;
+    out.qnodes.clear();
+    out.qnodes4.clear();
+    out.qnodes8.clear();
     for (uint32_t k = 0; k < src.n_objects; ++k) {
         const uint32_t id = src.objects[k];
         const float *p = sc.tri_pos + static_cast<size_t>(id) * 9;
@@ -311,7 +521,40 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     int rc = RT_OK;
     out.root = detail::pack_node(src, src.root, out, 0, rc);
     if (rc) return rc;
-    out.qnodes.clear();
+    if (formats & RT_PACK_Q8) {
+        if (formats != RT_PACK_Q8) return RT_ERR_INVALID_ARG;
+        std::vector<detail::Node8Boxes> boxes;
+        std::vector<uint32_t> perm, last;
+        perm.reserve(src.n_objects);
+        out.qnodes8.reserve(out.nodes.size() / 3 + 2);
+        detail::Collapse8 cl{out.nodes, out.tris, out.qnodes8, boxes, perm, last};
+        // root item: the box is not needed (the root's own box is never tested, bvh.h:170-180)
+        const float z[3] = {0.0f, 0.0f, 0.0f};
+        detail::Item8 root = cl.link_item(out.root, z, z);
+        if (root.link < 0) root = cl.range_item(root.tb, root.te);  // ... unless the root is a leaf: its box is a child box
+        out.qnodes8.emplace_back();
+        boxes.emplace_back();
+        cl.build(root, 0);
+        if (perm.size() != src.n_objects) return RT_ERR_BAD_SCENE;
+        if (int rq = detail::quantize_nodes8(boxes, out.qnodes8)) return rq;
+        std::vector<DTri> nt(src.n_objects);
+        std::vector<uint32_t> no(src.n_objects);
+        for (uint32_t k = 0; k < src.n_objects; ++k) {
+            nt[k] = out.tris[perm[k]];
+            nt[k].id_last &= ~RT_LAST_BIT;
+            no[k] = out.order[perm[k]];
+        }
+        for (uint32_t k : last) nt[k].id_last |= RT_LAST_BIT;
+        out.tris.swap(nt);
+        out.order.swap(no);
+        out.nodes.clear();  // their leaf links refer to the old triangle order
+        out.root = RT_LINK_NONE;
+        DTri null_tri;  // pair loads of the leaf phase may read one triangle past a leaf
+        std::memset(&null_tri, 0, sizeof null_tri);
+        null_tri.id_last = RT_LAST_BIT;
+        out.tris.push_back(null_tri);
+        return RT_OK;
+    }
     if (formats & RT_PACK_Q2)
         if (int rq = detail::quantize_nodes(out.nodes, out.qnodes)) return rq;
     // 4-wide collapse; the null leaf (absent children) is one degenerate triangle appended after the real ones
@@ -344,9 +587,11 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
     // light BVH: the traversal (all-hit light pdf) uses a rebuilt tree as well; the sampling list keeps the host's order
     {
         PackedBvh host_order;
-        if (int rc = pack_bvh(sc, sc.light_bvh, host_order, formats)) return rc;
+        if (int rc = pack_bvh(sc, sc.light_bvh, host_order, formats == RT_PACK_Q8 ? 0 : formats)) return rc;
         out.light_sample = host_order.tris;
-        if (rebuild_scene_bvh && sc.light_bvh.n_objects > 0 && sc.light_bvh.root != RT_NO_CHILD) {
+        if (formats == RT_PACK_Q8 && !(rebuild_scene_bvh && sc.light_bvh.n_objects > 0 && sc.light_bvh.root != RT_NO_CHILD)) {
+            if (int rc = pack_bvh(sc, sc.light_bvh, out.light, formats)) return rc;
+        } else if (rebuild_scene_bvh && sc.light_bvh.n_objects > 0 && sc.light_bvh.root != RT_NO_CHILD) {
             BuiltBvh built;
             build_sah_bvh(sc.tri_pos, sc.light_bvh.objects, sc.light_bvh.n_objects, built);
             if (int rc = pack_bvh(sc, built.desc(), out.light, formats)) return rc;
@@ -430,6 +675,8 @@ inline void fill_scene_constants(const rt_scene_desc &sc, const PackedScene &p, 
     d.scene.root = p.scene.root;
     d.scene.root4 = p.scene.root4;
     d.light.root4 = p.light.root4;
+    d.scene.n_nodes8 = static_cast<uint32_t>(p.scene.qnodes8.size());
+    d.light.n_nodes8 = static_cast<uint32_t>(p.light.qnodes8.size());
     d.scene.n_tris = static_cast<uint32_t>(p.scene.tris.size());
     d.light.root = p.light.root;
     d.light.n_tris = static_cast<uint32_t>(p.light.tris.size());

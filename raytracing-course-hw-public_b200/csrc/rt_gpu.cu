@@ -20,6 +20,15 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "extend8.cuh"
+#ifndef RT_EXT_WIDE8
+#define RT_EXT_WIDE8 0  // 1: k_extend8 over 8-wide nodes (extend8.cuh) instead of k_extend over 4-wide ones
+#endif
+#if RT_EXT_WIDE8
+#define RT_K_EXTEND rt::k_extend8
+#else
+#define RT_K_EXTEND rt::k_extend
+#endif
 #include "text_kernels.cuh"
 #include "repack.h"
 #include "rt_gpu.h"
@@ -110,6 +119,7 @@ struct DeviceState {
     // scene
     DevBuf<QNode> qnodes, lqnodes;  // scene BVH and light BVH, quantised (both traversed by k_extend)
     DevBuf<QNode4> qnodes4, lqnodes4;  // their 4-wide collapses
+    DevBuf<QNode8> qnodes8, lqnodes8;  // 8-wide (RT_EXT_WIDE8 builds)
     DevBuf<DTri> tris, ltris, lsample;
     DevBuf<DAttr> attrs;
     DevBuf<DTangent> tangents;
@@ -164,7 +174,10 @@ namespace {
 
 int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p) {
     CU_CHECK(cudaSetDevice(d.device));
-#if RT_EXT_WIDE4  // only the node format the traversal kernel was built for goes to the device
+#if RT_EXT_WIDE8  // only the node format the traversal kernel was built for goes to the device
+    if (int rc = d.qnodes8.upload(p.scene.qnodes8, d.stream)) return rc;
+    if (int rc = d.lqnodes8.upload(p.light.qnodes8, d.stream)) return rc;
+#elif RT_EXT_WIDE4
     if (int rc = d.qnodes4.upload(p.scene.qnodes4, d.stream)) return rc;
     if (int rc = d.lqnodes4.upload(p.light.qnodes4, d.stream)) return rc;
 #else
@@ -187,6 +200,8 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     d.scene.scene.qnodes = d.qnodes.p;
     d.scene.scene.qnodes4 = d.qnodes4.p;
     d.scene.light.qnodes4 = d.lqnodes4.p;
+    d.scene.scene.qnodes8 = d.qnodes8.p;
+    d.scene.light.qnodes8 = d.lqnodes8.p;
     d.scene.scene.tris = d.tris.p;
     d.scene.light.nodes = nullptr;
     d.scene.light.qnodes = d.lqnodes.p;
@@ -308,14 +323,15 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     }
     // Paths in flight per batch.  Every kernel of a batch ends with a tail in which the last warps finish
     // their rays while the other SMs idle, so throughput grows with the batch: 8 Mi / 16 / 32 / 64 / 128 /
-    // 256 Mi paths -> 771 / 819 / 845 / 881 / 896 / 910 Msamples/s on config 4 (B200, measured).  The default
-    // is 128 Mi paths (416 B of queue state each = 53 GB of the 180 GB), capped at half of the free memory.
+    // 256 Mi paths -> 771 / 819 / 845 / 881 / 896 / 910 Msamples/s on config 4 (B200, measured; a later build: 128 / 256 /
+    // 512 / 640 Mi -> 1149 / 1163 / 1169 / 1169).  The default is 512 Mi paths (132 B of queue state each = 71 GB of the
+    // 180 GB), capped at half of the free memory.
     const size_t px_begin = ids_mode ? 0 : rp.pixel_begin, px_end = ids_mode || rp.pixel_end == 0 ? n_pix : rp.pixel_end;
     const size_t n_render = px_end - px_begin;  // image-tile split: only this pixel range is rendered
     const size_t want_total = n_render * static_cast<size_t>(s_end - s_begin);
     size_t max_paths = rp.max_paths_in_flight;
     if (max_paths == 0) {
-        max_paths = static_cast<size_t>(128) << 20;
+        max_paths = static_cast<size_t>(512) << 20;
         // the memory query is a slow, jittery driver call (tens of ms with 50 GB allocated): only when the queues
         // would have to grow beyond what this handle already holds
         if (std::min(max_paths, want_total) > d.hit.n) {
@@ -375,7 +391,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
             rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q);
             mark(ctx, d, K_GENERATE);
             if (ids_mode) {  // pixel-centre rays through the same traversal kernel, then hit -> scene.objects id
-                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, 0, 0x3F800000u);
+                RT_K_EXTEND<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, 0, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
                 rt::k_ids_from_hits<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.hit.p, d.scene.scene.tris, d.prim_ids.p);
                 mark(ctx, d, K_IDS);
@@ -383,7 +399,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
                 continue;
             }
             for (uint32_t b = 0; b < depth; ++b) {
-                rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b, 0x3F800000u);
+                RT_K_EXTEND<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
                 rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b);
                 mark(ctx, d, K_SHADE);
@@ -439,7 +455,7 @@ int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device) {
         CU_CHECK(cudaEventCreate(&d->ev_red0));
         CU_CHECK(cudaEventCreate(&d->ev_red1));
         int occ_e = 0, occ_s = 0;
-        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, rt::k_extend, rt::kExtendThreads, 0));
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, RT_K_EXTEND, rt::kExtendThreads, 0));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, rt::k_shade, rt::kShadeThreads, 0));
         d->extend_blocks = d->sm_count * std::max(occ_e, 1);
         d->shade_blocks = d->sm_count * std::max(occ_s, 1);
@@ -467,7 +483,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        d.qnodes.release(); d.lqnodes.release(); d.qnodes4.release(); d.lqnodes4.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
+        d.qnodes.release(); d.lqnodes.release(); d.qnodes4.release(); d.lqnodes4.release(); d.qnodes8.release(); d.lqnodes8.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }
@@ -513,7 +529,7 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     const char *keep_env = std::getenv("RT_KEEP_HOST_BVH");  // A/B switch for measurements
     const bool keep = (scene->flags & RT_SCENE_KEEP_HOST_BVH) || (keep_env && std::atoi(keep_env) != 0);
     const auto t_pack0 = std::chrono::steady_clock::now();
-    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE4 ? rt::RT_PACK_Q4 : rt::RT_PACK_Q2)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : RT_EXT_WIDE4 ? rt::RT_PACK_Q4 : rt::RT_PACK_Q2)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
     const auto t_pack1 = std::chrono::steady_clock::now();
     for (auto &d : ctx->devs)
         if (int rc = upload_to_device(*d, *scene, packed)) return rc;

@@ -64,6 +64,30 @@ struct alignas(64) QNode4 {
     uint32_t pad[3];
 };
 
+// 8-wide quantised node (compressed wide BVH in the manner of Ylitie, Karras & Laine 2017, on this library's grid
+// encoding): 96 B = three 32-byte sectors.
+//   sector 0: grid origin words (as QNode), imask (bit s: the child in slot s is an inner node), index of the first
+//             inner child (inner children are consecutive in the node array, in slot order), index of the first
+//             triangle of the node's leaf children (consecutive in the triangle array, in slot order; the last
+//             triangle of each leaf child carries RT_LAST_BIT), counts: 2 bits per slot = triangles of the leaf
+//             child in that slot (1..3; 0 for an inner or empty slot)
+//   sector 1: children in slots 0..3: per axis the min-plane bytes and the max-plane bytes (six words)
+//   sector 2: children in slots 4..7
+// Slots are assigned by octant (slot bit k set = the child lies on the positive side along axis k), so that
+// `slot ^ octant-of-the-ray` orders the children front to back without any distance sort; empty slots carry an
+// inverted box.  The traversal stack holds (first child / first triangle, hit mask) groups instead of one entry per
+// child.  A BVH in this format has its triangles re-ordered (PackedBvh::order follows).
+struct alignas(32) QNode8 {
+    uint32_t org[3];
+    uint32_t imask;
+    uint32_t child_base;
+    uint32_t tri_base;
+    uint32_t counts;
+    uint32_t pad;
+    uint32_t g0[6], pad0[2];  // slots 0..3: lo x, lo y, lo z, hi x, hi y, hi z
+    uint32_t g1[6], pad1[2];  // slots 4..7
+};
+
 struct alignas(64) DTri {
     float ax, ay, az;
     uint32_t id_last;  // scene.objects index | RT_LAST_BIT on the last triangle of a leaf
@@ -112,6 +136,8 @@ struct DBvh {
     const QNode *qnodes;   // quantised 2-wide nodes
     const QNode4 *qnodes4; // quantised 4-wide nodes (collapsed tree) and their root link
     int32_t root4;
+    const QNode8 *qnodes8; // 8-wide nodes; node 0 is the root (n_nodes8 == 0: empty BVH)
+    uint32_t n_nodes8;
     const DTri *tris;
     int32_t root;  // link; RT_LINK_NONE when empty
     uint32_t n_tris;

@@ -20,10 +20,13 @@ struct HostScene {
 };
 
 bool g_rebuild = false;  // hc_set_rebuild: pack with the library's SAH builder instead of the host's tree
+bool g_wide8 = false;    // hc_set_wide8: pack the 8-wide node format (its own triangle order) and trace through it
 
 int build(const rt_scene_desc *sc, HostScene &hs) {
-    if (int rc = pack_scene(*sc, hs.p, g_rebuild)) return rc;
+    if (int rc = pack_scene(*sc, hs.p, g_rebuild, g_wide8 ? RT_PACK_Q8 : RT_PACK_ALL)) return rc;
     fill_scene_constants(*sc, hs.p, hs.d);
+    hs.d.scene.qnodes8 = hs.p.scene.qnodes8.data();
+    hs.d.light.qnodes8 = hs.p.light.qnodes8.data();
     hs.d.scene.nodes = hs.p.scene.nodes.data();
     hs.d.scene.qnodes = hs.p.scene.qnodes.data();
     hs.d.scene.qnodes4 = hs.p.scene.qnodes4.data();
@@ -40,6 +43,11 @@ int build(const rt_scene_desc *sc, HostScene &hs) {
     hs.d.textures = hs.p.textures.data();
     hs.d.texels = hs.p.texels.data();
     return 0;
+}
+
+// the closest hit through whichever node format the scene was packed with
+Hit trace(const DBvh &bvh, f3 o, f3 d, float eps) {
+    return bvh.n_nodes8 ? closest_hit_q8(bvh, o, d, eps, nullptr) : closest_hit(bvh, o, d, eps);
 }
 
 Camera make_camera(const DScene &d, uint32_t w, uint32_t h) {
@@ -60,6 +68,42 @@ Camera make_camera(const DScene &d, uint32_t w, uint32_t h) {
 extern "C" {
 
 void hc_set_rebuild(int on) { g_rebuild = on != 0; }
+void hc_set_wide8(int on) { g_wide8 = on != 0; }
+
+// Structure of the 8-wide collapse and node steps of its traversal over the pixel-centre rays:
+// out[0] nodes, out[1] mean children per node, out[2] node steps per ray, out[3] triangles (must equal the scene's)
+int hc_wide8_stats(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids, double *out) {
+    const bool keep = g_wide8;
+    g_wide8 = true;
+    HostScene hs;
+    const int rc = build(sc, hs);
+    g_wide8 = keep;
+    if (rc) return rc;
+    const Camera cam = make_camera(hs.d, w, h);
+    uint64_t steps = 0;
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
+            uint32_t st = 0;
+            const Hit hit = closest_hit_q8(hs.d.scene, cam.pos, dir, hs.d.eps, &st);
+            steps += st;
+            ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
+        }
+    uint64_t kids = 0, tris = 0;
+    for (const QNode8 &q : hs.p.scene.qnodes8) {
+        kids += __builtin_popcount(q.imask & 0xFFu);
+        for (int s = 0; s < 8; ++s) {
+            const uint32_t c = (q.counts >> (2 * s)) & 3u;
+            kids += c ? 1 : 0;
+            tris += c;
+        }
+    }
+    out[0] = (double)hs.p.scene.qnodes8.size();
+    out[1] = hs.p.scene.qnodes8.empty() ? 0.0 : (double)kids / (double)hs.p.scene.qnodes8.size();
+    out[2] = (double)steps / ((double)w * h);
+    out[3] = (double)tris;
+    return 0;
+}
 
 // Build statistics of the library's SAH builder: out[0] = seconds, out[1] = inner nodes, out[2] = leaves,
 // out[3] = max leaf size, out[4] = max depth, out[5] = 1 when every triangle id appears exactly once.
@@ -122,7 +166,7 @@ int hc_primary_ids(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids
     for (uint32_t y = 0; y < h; ++y)
         for (uint32_t x = 0; x < w; ++x) {
             const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
-            const Hit hit = closest_hit(hs.d.scene, cam.pos, dir, hs.d.eps);
+            const Hit hit = trace(hs.d.scene, cam.pos, dir, hs.d.eps);
             ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
         }
     return 0;
@@ -242,7 +286,7 @@ int hc_hitinfo(const rt_scene_desc *sc, uint32_t w, uint32_t h, float *out) {
     for (uint32_t y = 0; y < h; ++y)
         for (uint32_t x = 0; x < w; ++x) {
             const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
-            const Hit hit = closest_hit(hs.d.scene, cam.pos, dir, hs.d.eps);
+            const Hit hit = trace(hs.d.scene, cam.pos, dir, hs.d.eps);
             if (hit.tri < 0) continue;
             const Surface sf = make_surface(hs.d, hs.p.gamma_lut, hit, dir);
             float *o = out + ((size_t)y * w + x) * 18;
@@ -274,7 +318,7 @@ int hc_render(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint32_t samples,
             f3 d = camera_dir(cam, (float)(pix % w) + u01(j.x), (float)(pix / w) + u01(j.y));
             f3 thr = mk3(1, 1, 1), rad = mk3(0, 0, 0);
             for (uint32_t b = 0; b < hs.d.ray_depth; ++b) {
-                const Hit hit = closest_hit(hs.d.scene, o, d, hs.d.eps);
+                const Hit hit = trace(hs.d.scene, o, d, hs.d.eps);
                 ++ext;
                 uint32_t lr = 0;
                 const bool alive = shade_bounce(hs.d, hs.p.gamma_lut, key, b, b + 1 == hs.d.ray_depth, hit, o, d, thr, rad, lr);

@@ -272,6 +272,45 @@ def test_four_wide_collapse_on_the_260k_scene(hc, big_scene):
     assert steps[0] < 0.6 * steps[1]  # measured 0.53: the collapse nearly halves the node steps
 
 
+@pytest.mark.parametrize("rebuild", [0, 1])
+@pytest.mark.parametrize("name", SMALL)
+def test_eight_wide_traversal_gives_reference_ids(name, rebuild, hc, manifest, golden_scene):
+    """The 8-wide collapse (QNode8: octant-ordered slots, group stack, re-ordered triangles) finds the reference's hits
+    and holds every triangle exactly once."""
+    m = manifest["scenes"][name]
+    w, h = m["width"], m["height"]
+    sc = golden_scene(name)
+    d = sc.desc()
+    ids = np.zeros((h, w), np.int32)
+    out = (C.c_double * 4)()
+    hc.hc_set_rebuild(rebuild)
+    try:
+        assert hc.hc_wide8_stats(C.byref(d), w, h, ids.ctypes.data_as(C.c_void_p), out) == 0
+    finally:
+        hc.hc_set_rebuild(0)
+    ref = golden_array(f"{name}_ids.i32", np.int32, (h, w))
+    assert (ids == ref).mean() >= 0.999
+    assert int(out[3]) == d.n_tris
+
+
+def test_eight_wide_collapse_on_the_260k_scene(hc, big_scene):
+    d = big_scene.desc()
+    ids8 = np.zeros((96, 96), np.int32)
+    ids2 = np.zeros((96, 96), np.int32)
+    out = (C.c_double * 4)()
+    steps = (C.c_uint64 * 2)()
+    hc.hc_set_rebuild(1)
+    try:
+        assert hc.hc_wide8_stats(C.byref(d), 96, 96, ids8.ctypes.data_as(C.c_void_p), out) == 0
+        assert hc.hc_primary_ids_q4(C.byref(d), 96, 96, ids2.ctypes.data_as(C.c_void_p), steps) == 0
+    finally:
+        hc.hc_set_rebuild(0)
+    assert (ids8 == ids2).mean() >= 0.999
+    assert int(out[3]) == d.n_tris
+    assert out[1] > 4.0  # children per wide node (measured 4.5: the bottom of the tree holds quads, 2 triangles per leaf)
+    assert out[2] * 96 * 96 < 0.8 * steps[0]  # fewer node steps than the 4-wide traversal of the same rays
+
+
 def test_device_philox_matches_known_answers(hc):
     out = (C.c_uint32 * 4)()
     hc.hc_philox((C.c_uint32 * 4)(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344),
@@ -294,6 +333,19 @@ def test_device_hit_data_matches_reference(name, hc, manifest, golden_scene):
     diff[:, 0] /= np.maximum(ref[hit][:, 0], 1.0)  # t relative
     assert np.quantile(diff, 0.999) < 1e-4
     assert diff.max() < 5e-3
+
+
+@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.01), ("small_lights", 0.02)])
+def test_device_math_follows_oracle_paths_eight_wide(name, tol_frac, hc, manifest, golden_scene):
+    """The same path-by-path comparison with the scene packed in the 8-wide format (own triangle order, light pdf summed
+    over the 8-wide light BVH)."""
+    hc.hc_set_rebuild(1)
+    hc.hc_set_wide8(1)
+    try:
+        _follow_oracle_paths(name, tol_frac, hc, manifest, golden_scene)
+    finally:
+        hc.hc_set_rebuild(0)
+        hc.hc_set_wide8(0)
 
 
 @pytest.mark.parametrize("rebuild", [0, 1])
