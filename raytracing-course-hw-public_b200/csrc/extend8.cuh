@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT8_MINB)
         const bool idle = gy == 0 && gx == kDone8 && ty == 0;
         if (idle && ray != kNoRay) {
             const uint32_t r = ray & 0x7FFFFFFFu;
-            if (ray >> 31) q.lpdf[r] = lsum * inv_n_lights;
-            q.hit[r] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
+            if (ray >> 31) q_store<0>(q.lpdf + r, lsum * inv_n_lights);
+            q_store<0>(q.hit + r, make_float4(best_t, best_b, best_c, __int_as_float(best_tri)));
             ray = kNoRay;
         }
         const uint32_t m_idle = __ballot_sync(FULL, idle);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT8_MINB)
             const uint32_t rank = static_cast<uint32_t>(__popc(m_idle & lt_mask));
             if (idle && rank < take) {
                 ray = pool_next + rank;
-                const float4 o4 = qo[ray], d4 = qd[ray];
+                const float4 o4 = q_load<0>(qo + ray), d4 = q_load<0>(qd + ray);
                 o = mk3(o4.x, o4.y, o4.z);
                 d = mk3(d4.x, d4.y, d4.z);
                 idir = mk3(rcp_rn(d.x), rcp_rn(d.y), rcp_rn(d.z));

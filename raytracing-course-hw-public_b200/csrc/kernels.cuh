@@ -50,6 +50,27 @@ struct Queues {
     float *lpdf;                // light pdf of the queued ray (bvh_mix_dist::pdf), written by k_extend for pending paths
 };
 
+// Queue records are read once and written once per bounce (streaming), the scene is re-read by every ray: with
+// RT_QUEUE_STREAMING the queue accesses carry the evict-first hint (ld/st.global.cs) so that they do not push nodes,
+// triangles and attributes out of the L2.  Measured on the B200 (k_extend / k_shade ms per 128 spp): off 84.9 / 25.7,
+// k_extend's accesses only 84.0 / 25.8 (the default), everything incl. the radiance sums 83.7 / 28.6.  An explicit L2
+// persisting window over the scene arrays (cudaAccessPropertyPersisting) changed nothing and was removed.
+#ifndef RT_QUEUE_STREAMING
+#define RT_QUEUE_STREAMING 1
+#endif
+// bit 0: k_extend's ray loads and hit stores; bit 1: k_shade's record loads; bit 2: k_shade's / k_generate's record
+// stores; bit 3: the radiance accumulator
+template <int BIT> __device__ __forceinline__ float4 q_load(const float4 *p) { return (RT_QUEUE_STREAMING >> BIT) & 1 ? __ldcs(p) : *p; }
+template <int BIT> __device__ __forceinline__ float q_load(const float *p) { return (RT_QUEUE_STREAMING >> BIT) & 1 ? __ldcs(p) : *p; }
+template <int BIT> __device__ __forceinline__ void q_store(float4 *p, float4 v) {
+    if ((RT_QUEUE_STREAMING >> BIT) & 1) __stcs(p, v);
+    else *p = v;
+}
+template <int BIT> __device__ __forceinline__ void q_store(float *p, float v) {
+    if ((RT_QUEUE_STREAMING >> BIT) & 1) __stcs(p, v);
+    else *p = v;
+}
+
 constexpr int kExtendThreads = 128;
 constexpr int kShadeThreads = 128;
 
@@ -92,10 +113,10 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
         jy = u01(r.y);
     }
     const f3 dir = camera_dir(cam, static_cast<float>(px) + jx, static_cast<float>(py) + jy);
-    q.o[0][slot] = make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel));
-    q.d[0][slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample));
-    q.thr[0][slot] = make_float4(1.0f, 1.0f, 1.0f, -1.0f);
-    q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    q_store<2>(q.o[0] + slot, make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel)));
+    q_store<2>(q.d[0] + slot, make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample)));
+    q_store<2>(q.thr[0] + slot, make_float4(1.0f, 1.0f, 1.0f, -1.0f));
+    q_store<3>(q.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
 // ---- k_extend -----------------------------------------------------------------------------------------
@@ -234,8 +255,8 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
 #if RT_EXT_INLINE_LMODE
         if (idle && ray != kNoRay) {  // bit 31 of `ray`: pending, its light pdf is wanted (0 without a light BVH)
             const uint32_t r = ray & 0x7FFFFFFFu;
-            if (ray >> 31) q.lpdf[r] = lsum * inv_n_lights;
-            q.hit[r] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
+            if (ray >> 31) q_store<0>(q.lpdf + r, lsum * inv_n_lights);
+            q_store<0>(q.hit + r, make_float4(best_t, best_b, best_c, __int_as_float(best_tri)));
             ray = kNoRay;
         }
 #else
@@ -273,7 +294,7 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             const uint32_t rank = static_cast<uint32_t>(__popc(m_idle & lt_mask));
             if (idle && rank < take) {
                 ray = pool_next + rank;
-                const float4 o4 = qo[ray], d4 = qd[ray];
+                const float4 o4 = q_load<0>(qo + ray), d4 = q_load<0>(qd + ray);
                 o = mk3(o4.x, o4.y, o4.z);
                 d = mk3(d4.x, d4.y, d4.z);
                 idir = mk3(rcp_rn(d.x), rcp_rn(d.y), rcp_rn(d.z));
@@ -531,14 +552,14 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
         float pending = -1.0f;
         uint32_t pixel = 0, sample = 0;
         if (i < count) {
-            const float4 o4 = q.o[in][i], d4 = q.d[in][i], t4 = q.thr[in][i], h4 = q.hit[i];
+            const float4 o4 = q_load<1>(q.o[in] + i), d4 = q_load<1>(q.d[in] + i), t4 = q_load<1>(q.thr[in] + i), h4 = q_load<1>(q.hit + i);
             o = mk3(o4.x, o4.y, o4.z);
             d = mk3(d4.x, d4.y, d4.z);
             thr = mk3(t4.x, t4.y, t4.z);
             pixel = __float_as_uint(o4.w);
             sample = __float_as_uint(d4.w) & 0x7FFFFFFFu;
             bool live = true;
-            if (__float_as_uint(d4.w) >> 31) live = shade_resolve(s, thr, t4.w, q.lpdf[i], thr);  // previous bounce
+            if (__float_as_uint(d4.w) >> 31) live = shade_resolve(s, thr, t4.w, q_load<1>(q.lpdf + i), thr);  // previous bounce
             if (live) {
                 ++n_ext;  // this extension ray's hit is consumed (cast_ray of the reference)
                 Hit h;
@@ -569,19 +590,19 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
                 }
                 if (rad.x != 0.0f || rad.y != 0.0f || rad.z != 0.0f) {  // NaN != 0 is true: poisons the sample like the reference
                     const uint32_t slot = (sample - bp.s0) * bp.npix + (pixel - bp.pix0);
-                    float4 acc = q.rad[slot];
+                    float4 acc = q_load<3>(q.rad + slot);
                     acc.x += rad.x;
                     acc.y += rad.y;
                     acc.z += rad.z;
-                    q.rad[slot] = acc;
+                    q_store<3>(q.rad + slot, acc);
                 }
             }
         }
         const uint32_t dst = warp_append(q.count + bounce + 1, alive);
         if (alive) {
-            q.o[out][dst] = make_float4(o.x, o.y, o.z, __uint_as_float(pixel));
-            q.d[out][dst] = make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u)));
-            q.thr[out][dst] = make_float4(thr.x, thr.y, thr.z, pending);
+            q_store<2>(q.o[out] + dst, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+            q_store<2>(q.d[out] + dst, make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u))));
+            q_store<2>(q.thr[out] + dst, make_float4(thr.x, thr.y, thr.z, pending));
         }
     }
     // block-level reduction of the work counters -> one atomic per CTA and counter
@@ -608,7 +629,7 @@ __global__ void __launch_bounds__(256) k_accumulate(BatchParams bp, const float4
     if (p >= bp.npix) return;
     f3 sum = mk3(0, 0, 0);
     for (uint32_t j = 0; j < bp.k; ++j) {
-        const float4 v = rad[static_cast<size_t>(j) * bp.npix + p];
+        const float4 v = q_load<3>(rad + static_cast<size_t>(j) * bp.npix + p);
         sum = sum + sanitize(mk3(v.x, v.y, v.z));
     }
     float4 a = accum[bp.pix0 + p];
