@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -41,6 +42,24 @@ struct PackedScene {
     std::vector<DTex> textures;
     std::vector<uint32_t> texels;
     float gamma_lut[256];  // powf(k/255, 2.2f): the per-texel pow of Texture::sample (geometry.h:525-527,561)
+    // working memory of the library's BVH builder, kept with the staging arrays (re-used by the next pack_scene)
+    BuiltBvh built;
+    sah::Ctx sah_scratch;
+};
+
+// optional phase timers (ms) of pack_scene, for RT_TIMING=1 and the host timing test: [0] SAH build (scene),
+// [1] triangles + binary nodes, [2] wide collapse, [3] quantisation, [4] light BVHs, [5] attributes, [6] materials/texels
+inline double *&pack_times() {
+    static thread_local double *p = nullptr;
+    return p;
+}
+struct PackLap {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(int slot) {
+        const auto n = std::chrono::steady_clock::now();
+        if (pack_times()) pack_times()[slot] += std::chrono::duration<double, std::milli>(n - t).count();
+        t = n;
+    }
 };
 
 namespace detail {
@@ -506,21 +525,25 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     out.qnodes.clear();
     out.qnodes4.clear();
     out.qnodes8.clear();
-    for (uint32_t k = 0; k < src.n_objects; ++k) {
-        const uint32_t id = src.objects[k];
-        const float *p = sc.tri_pos + static_cast<size_t>(id) * 9;
-        DTri &t = out.tris[k];
-        t.ax = p[0]; t.ay = p[1]; t.az = p[2];
-        t.e1x = p[3] - p[0]; t.e1y = p[4] - p[1]; t.e1z = p[5] - p[2];
-        t.e2x = p[6] - p[0]; t.e2y = p[7] - p[1]; t.e2z = p[8] - p[2];
-        t.pad0 = t.pad1 = 0.0f;
-        t.pad2[0] = t.pad2[1] = t.pad2[2] = t.pad2[3] = 0.0f;
-        t.id_last = id;
-    }
+    PackLap lap;
+    detail::parallel_for(src.n_objects, [&](size_t kb, size_t ke) {
+        for (size_t k = kb; k < ke; ++k) {
+            const uint32_t id = src.objects[k];
+            const float *p = sc.tri_pos + static_cast<size_t>(id) * 9;
+            DTri &t = out.tris[k];
+            t.ax = p[0]; t.ay = p[1]; t.az = p[2];
+            t.e1x = p[3] - p[0]; t.e1y = p[4] - p[1]; t.e1z = p[5] - p[2];
+            t.e2x = p[6] - p[0]; t.e2y = p[7] - p[1]; t.e2z = p[8] - p[2];
+            t.pad0 = t.pad1 = 0.0f;
+            t.pad2[0] = t.pad2[1] = t.pad2[2] = t.pad2[3] = 0.0f;
+            t.id_last = id;
+        }
+    });
     if (src.root == RT_NO_CHILD || src.n_objects == 0) return RT_OK;
     int rc = RT_OK;
     out.root = detail::pack_node(src, src.root, out, 0, rc);
     if (rc) return rc;
+    lap.lap(1);
     if (formats & RT_PACK_Q8) {
         if (formats != RT_PACK_Q8) return RT_ERR_INVALID_ARG;
         std::vector<detail::Node8Boxes> boxes;
@@ -569,7 +592,9 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
         out.qnodes4.reserve(out.nodes.size() / 2 + 1);
         boxes.reserve(out.nodes.size() / 2 + 1);
         out.root4 = detail::collapse4(out.nodes, out.root, null_leaf, out.qnodes4, boxes);
+        lap.lap(2);
         if (int rq = detail::quantize_nodes4(boxes, out.qnodes4)) return rq;
+        lap.lap(3);
     }
     return rc;
 }
@@ -577,10 +602,11 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
 // `rebuild_scene_bvh`: build the scene BVH with the library's SAH builder (sah_build.h) over the triangles of
 // sc.scene_bvh instead of adopting the host's tree; the light BVH is always adopted as passed.
 inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false, int formats = RT_PACK_ALL) {
+    PackLap lap;
     if (rebuild_scene_bvh && sc.scene_bvh.n_objects > 0 && sc.scene_bvh.root != RT_NO_CHILD) {
-        BuiltBvh built;
-        build_sah_bvh(sc.tri_pos, sc.scene_bvh.objects, sc.scene_bvh.n_objects, built);
-        if (int rc = pack_bvh(sc, built.desc(), out.scene, formats)) return rc;
+        build_sah_bvh(sc.tri_pos, sc.scene_bvh.objects, sc.scene_bvh.n_objects, out.built, &out.sah_scratch);
+        lap.lap(0);
+        if (int rc = pack_bvh(sc, out.built.desc(), out.scene, formats)) return rc;
     } else if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene, formats)) {
         return rc;
     }
@@ -600,6 +626,7 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
         }
     }
 
+    lap = PackLap();
     const uint32_t n = static_cast<uint32_t>(out.scene.order.size());  // device triangle order = packed BVH order
     out.attrs.resize(n);
     bool any_tangent = false;
@@ -610,26 +637,28 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
         }
     out.tangents.clear();
     if (any_tangent) out.tangents.resize(n);
-    for (uint32_t k = 0; k < n; ++k) {
-        const uint32_t id = out.scene.order[k];
-        const float *nn = sc.tri_normals + static_cast<size_t>(id) * 9;
-        const float *uv = sc.tri_uv + static_cast<size_t>(id) * 6;
-        DAttr &a = out.attrs[k];
-        a.n0x = nn[0]; a.n0y = nn[1]; a.n0z = nn[2];
-        a.n1x = nn[3]; a.n1y = nn[4]; a.n1z = nn[5];
-        a.n2x = nn[6]; a.n2y = nn[7]; a.n2z = nn[8];
-        a.uv0x = uv[0]; a.uv0y = uv[1]; a.uv1x = uv[2]; a.uv1y = uv[3]; a.uv2x = uv[4]; a.uv2y = uv[5];
-        a.material = sc.tri_material[id];
-        if (any_tangent) {
-            const float *t = sc.tri_tangents + static_cast<size_t>(id) * 9;
-            DTangent &d = out.tangents[k];
-            d.t0x = t[0]; d.t0y = t[1]; d.t0z = t[2];
-            d.t1x = t[3]; d.t1y = t[4]; d.t1z = t[5];
-            d.t2x = t[6]; d.t2y = t[7]; d.t2z = t[8];
-            d.pad0 = d.pad1 = d.pad2 = 0.0f;
+    detail::parallel_for(n, [&](size_t kb, size_t ke) {
+        for (size_t k = kb; k < ke; ++k) {
+            const uint32_t id = out.scene.order[k];
+            const float *nn = sc.tri_normals + static_cast<size_t>(id) * 9;
+            const float *uv = sc.tri_uv + static_cast<size_t>(id) * 6;
+            DAttr &a = out.attrs[k];
+            a.n0x = nn[0]; a.n0y = nn[1]; a.n0z = nn[2];
+            a.n1x = nn[3]; a.n1y = nn[4]; a.n1z = nn[5];
+            a.n2x = nn[6]; a.n2y = nn[7]; a.n2z = nn[8];
+            a.uv0x = uv[0]; a.uv0y = uv[1]; a.uv1x = uv[2]; a.uv1y = uv[3]; a.uv2x = uv[4]; a.uv2y = uv[5];
+            a.material = sc.tri_material[id];
+            if (any_tangent) {
+                const float *t = sc.tri_tangents + static_cast<size_t>(id) * 9;
+                DTangent &d = out.tangents[k];
+                d.t0x = t[0]; d.t0y = t[1]; d.t0z = t[2];
+                d.t1x = t[3]; d.t1y = t[4]; d.t1z = t[5];
+                d.t2x = t[6]; d.t2y = t[7]; d.t2z = t[8];
+                d.pad0 = d.pad1 = d.pad2 = 0.0f;
+            }
         }
-    }
-
+    });
+    lap.lap(5);
     out.light_extra.resize(sc.light_bvh.n_objects);
     for (uint32_t k = 0; k < sc.light_bvh.n_objects; ++k) {
         const DTri &t = out.light.tris[k];
@@ -666,6 +695,7 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
                            sc.textures[i].height, 0};
     }
     for (int k = 0; k < 256; ++k) out.gamma_lut[k] = std::pow(static_cast<float>(k) / 255.0f, 2.2f);
+    lap.lap(6);
     return RT_OK;
 }
 

@@ -23,6 +23,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -55,6 +56,21 @@ constexpr uint32_t kMaxLeaf = 8;
 constexpr float kTraversalCost = 1.0f;
 constexpr uint32_t kParallelMin = 8192;  // sub-trees at least this large may get their own thread
 constexpr int kParallelDepth = 5;        // ... down to this depth (<= 32 threads)
+
+// fn(begin, end) over [0, n) on up to 16 threads
+template <class F> inline void parallel_chunks(uint32_t n, F fn) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint32_t nt = std::max(1u, std::min(std::min(hw ? hw : 1u, 16u), n / 16384u));
+    if (nt <= 1) {
+        fn(0u, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const uint32_t chunk = (n + nt - 1) / nt;
+    for (uint32_t t = 1; t < nt; ++t) th.emplace_back([=] { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk)); });
+    fn(0u, std::min(n, chunk));
+    for (auto &x : th) x.join();
+}
 
 struct Box3 {
     float lo[3], hi[3];
@@ -275,39 +291,64 @@ inline void build_range(Ctx &cx, uint32_t slot, uint32_t b, uint32_t e, const Bo
 
 }  // namespace sah
 
-// Builds a BVH over the triangles `ids` (indices into tri_pos, 9 floats per triangle).
-inline void build_sah_bvh(const float *tri_pos, const uint32_t *ids, uint32_t n, BuiltBvh &out) {
+// Builds a BVH over the triangles `ids` (indices into tri_pos, 9 floats per triangle).  `scratch`: working arrays a caller
+// that builds repeatedly keeps alive, so that their memory is allocated and touched only once.
+inline void build_sah_bvh(const float *tri_pos, const uint32_t *ids, uint32_t n, BuiltBvh &out, sah::Ctx *scratch = nullptr) {
     out.nodes.clear();
     out.objects.clear();
     out.root = RT_NO_CHILD;
     if (n == 0) return;
-    sah::Ctx cx;
+    sah::Ctx local;
+    sah::Ctx &cx = scratch ? *scratch : local;
     cx.prims.resize(n);
     sah::Box3 box, cbox;
     box.reset();
     cbox.reset();
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t id = ids ? ids[i] : i;
-        const float *p = tri_pos + static_cast<size_t>(id) * 9;
-        sah::Prim &pr = cx.prims[i];
-        for (int k = 0; k < 3; ++k) {
-            const float a = p[k], b2 = p[3 + k], c = p[6 + k];
-            pr.lo[k] = std::min(a, std::min(b2, c));
-            pr.hi[k] = std::max(a, std::max(b2, c));
-            pr.c[k] = 0.5f * (pr.lo[k] + pr.hi[k]);
-        }
-        pr.id = id;
-        box.grow(pr.lo, pr.hi);
-        cbox.grow(pr.c, pr.c);
+    {  // per-triangle boxes and centroids, in parallel; the scene box is merged from the chunks' boxes
+        std::mutex mu;
+        sah::parallel_chunks(n, [&](uint32_t b, uint32_t e) {
+            sah::Box3 lb, lc;
+            lb.reset();
+            lc.reset();
+            for (uint32_t i = b; i < e; ++i) {
+                const uint32_t id = ids ? ids[i] : i;
+                const float *p = tri_pos + static_cast<size_t>(id) * 9;
+                sah::Prim &pr = cx.prims[i];
+                for (int k = 0; k < 3; ++k) {
+                    const float a = p[k], b2 = p[3 + k], c = p[6 + k];
+                    pr.lo[k] = std::min(a, std::min(b2, c));
+                    pr.hi[k] = std::max(a, std::max(b2, c));
+                    pr.c[k] = 0.5f * (pr.lo[k] + pr.hi[k]);
+                }
+                pr.id = id;
+                lb.grow(pr.lo, pr.hi);
+                lc.grow(pr.c, pr.c);
+            }
+            std::lock_guard<std::mutex> g(mu);
+            box.grow(lb);
+            cbox.grow(lc);
+        });
     }
     rt_bvh_node blank;
     std::memset(&blank, 0, sizeof blank);
     blank.left_child = blank.right_child = RT_NO_CHILD;
-    cx.nodes.assign(static_cast<size_t>(2) * n - 1, blank);
+    cx.nodes.resize(static_cast<size_t>(2) * n - 1);
+    {
+        rt_bvh_node *nodes = cx.nodes.data();
+        sah::parallel_chunks(2 * n - 1, [=](uint32_t b, uint32_t e) {
+            for (uint32_t i = b; i < e; ++i) nodes[i] = blank;
+        });
+    }
     sah::build_range(cx, 0, 0, n, box, cbox, 0);
     out.nodes.swap(cx.nodes);
     out.objects.resize(n);
-    for (uint32_t i = 0; i < n; ++i) out.objects[i] = cx.prims[i].id;
+    {
+        uint32_t *obj = out.objects.data();
+        const sah::Prim *prims = cx.prims.data();
+        sah::parallel_chunks(n, [=](uint32_t b, uint32_t e) {
+            for (uint32_t i = b; i < e; ++i) obj[i] = prims[i].id;
+        });
+    }
     out.root = 0;
 }
 

@@ -1,5 +1,5 @@
 import os, sys, time
-sys.path[:0] = ['/root/repo', '/root/repo/scenes']
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'scenes')]
 os.environ['RT_TIMING']='1'
 import bench, rt_b200
 from rt_b200 import gltf as gl, gpu
