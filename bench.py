@@ -201,8 +201,15 @@ def run_reference_arm(args, rank):
 
 
 def config_dict(n_gpus, extra=None):
-    c = {"workload": f"BASELINE config 4: synthetic Sponza-scale glTF '{SCENE}' (260192 triangles, textured, 32 "
-                     f"emissive), {WIDTH}x{HEIGHT}, {SPP_PER_GPU} spp per GPU, ray depth 8",
+    e = extra or {}
+    w, h, spp = e.get("width", WIDTH), e.get("height", HEIGHT), e.get("spp_per_gpu", SPP_PER_GPU)
+    name = "BASELINE config 4"
+    if (w, h) == (3840, 2160) and spp * n_gpus == 4096:
+        name = "BASELINE config 5"
+    elif (w, h, spp) != (WIDTH, HEIGHT, SPP_PER_GPU):
+        name = "BASELINE config 4 scene at a non-default size"
+    c = {"workload": f"{name}: synthetic Sponza-scale glTF '{e.get('scene', SCENE)}' (260192 triangles, textured, 32 "
+                     f"emissive), {w}x{h}, {spp} spp per GPU, ray depth 8",
          "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP_PER_GPU, "spp_total": SPP_PER_GPU * n_gpus,
          "parallelism": f"sample-split x{n_gpus} + 1 NCCL reduce" if n_gpus > 1 else "single GPU",
          "l2": "256 MiB written between steps; per-step path-queue traffic (>100 GB) far exceeds the 126 MB L2"}

@@ -28,7 +28,7 @@ namespace rt {
 #define RT_EXT8_MINB 8
 #endif
 #ifndef RT_EXT8_MIN_SEARCH
-#define RT_EXT8_MIN_SEARCH 20
+#define RT_EXT8_MIN_SEARCH 16  // 16 / 20 / 24 -> 95.5 / 98.1 / 101.2 ms of k_extend8 per 128 spp
 #endif
 #ifndef RT_EXT8_STEPS_PER_VOTE
 #define RT_EXT8_STEPS_PER_VOTE 2

@@ -254,3 +254,22 @@ def test_cli_drop_in_matches_reference_binary(scene_dir, tmp_path):
             assert img.shape == ref.shape
             mae = np.abs(img.astype(int) - ref.astype(int)).mean()
             assert mae < 1.0, (name, mae)  # tiny scene: 0.52 LSB reference-vs-reference at 4096 spp
+
+
+def test_eight_wide_build_keeps_parity():
+    """The optional 8-wide traversal build (k_extend8, -DRT_EXT_WIDE8=1) passes the same id / path-by-path / statistical
+    parity tests; it is loaded through RT_GPU_LIB in a fresh interpreter."""
+    import subprocess
+    import sys
+
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(ROOT, "raytracing-course-hw-public_b200", "librt_gpu_wide8.so")
+    if not os.path.exists(lib):
+        pytest.fail("librt_gpu_wide8.so is missing: run __graft_entry__.build()")
+    if os.environ.get("RT_GPU_LIB"):
+        pytest.skip("already running against an alternative build")
+    env = dict(os.environ, RT_GPU_LIB=lib)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "primary_ids or paths_follow_oracle or statistical_parity_small or determinism"],
+                       env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
