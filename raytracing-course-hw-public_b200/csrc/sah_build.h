@@ -53,7 +53,12 @@ namespace sah {
 constexpr int kBins = 32;
 constexpr uint32_t kMaxLeaf = 8;
 // in triangle tests; 0.5 / 1 / 1.5 measured equal on the B200 (k_extend 86.9 ms), 2 -> 91.6, 3 -> 95.9
-constexpr float kTraversalCost = 1.0f;
+// (the 8-wide build, whose node step costs 1.5x the 4-wide one, does not want larger leaves either:
+// 1 / 2 / 3 / 5 -> 94.4 / 100.2 / 113.7 / 115.8 ms of k_extend8 per 128 spp)
+#ifndef RT_SAH_TRAVERSAL_COST
+#define RT_SAH_TRAVERSAL_COST 1.0f
+#endif
+constexpr float kTraversalCost = RT_SAH_TRAVERSAL_COST;
 constexpr uint32_t kParallelMin = 8192;  // sub-trees at least this large may get their own thread
 constexpr int kParallelDepth = 5;        // ... down to this depth (<= 32 threads)
 
