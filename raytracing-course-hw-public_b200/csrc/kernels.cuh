@@ -120,33 +120,41 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
 }
 
 // ---- k_extend -----------------------------------------------------------------------------------------
-// Closest-hit traversal, warp-synchronous "while-while" with one postponed leaf per lane (Aila & Laine
-// 2009 style speculative traversal) and per-lane ray refill:
+// Closest-hit traversal over the 4-wide quantised nodes (QNode4), warp-synchronous "while-while" with one postponed
+// leaf per lane (Aila & Laine 2009 style speculative traversal) and per-lane ray refill:
 //   * every loop condition is a warp vote (__any_sync / __ballot_sync), so the 32 lanes re-converge at
 //     each phase boundary instead of drifting apart (the naive per-thread loop ran its triangle tests
 //     with 2 of 32 lanes active);
-//   * inner phase: one iteration = at most one stack pop, then at most one node step per lane, all
-//     predicated (no per-lane loops: the pop-until-useful loop of the first version ran with 2 of 32 lanes
-//     active and was 9 % of the kernel's instructions).  The first leaf a lane meets is postponed and the
+//   * inner phase: one iteration = at most one stack pop, then at most one node step per lane, then the leaf
+//     check, all predicated (no per-lane loops: the pop-until-useful loop of the first version ran with 2 of 32
+//     lanes active and was 9 % of the kernel's instructions).  The first leaf a lane meets is postponed and the
 //     lane keeps descending speculatively; a lane that meets a second leaf waits.  The phase ends when fewer
 //     than kMinSearching lanes are still looking for their first leaf;
-//   * leaf phase: all postponed leaves are intersected together, triangle by triangle;
+//   * leaf phase: all postponed leaves are intersected together, two triangles per iteration;
 //   * a lane whose ray is finished stores its hit and takes the next ray from a warp-local block of
 //     kRayBlock queue entries (one atomicAdd per block), ranks handed out with __ballot_sync/__popc.
 // Visiting order (near child first, ties left first, bvh.h:216) and strictly-closer-wins (bvh.h:132)
-// are those of closest_hit() in pt_core.cuh, so both give the same hit.
+// are those of closest_hit_q4() in pt_core.cuh, so both give the same hit.
 //
-// Compile-time knobs (A/B-tested on the B200, DESIGN.md "k_extend"; defaults = the fastest measured):
-// (64-byte full-precision nodes were the other candidate: equal within 4 % once the kernel was issue-bound, and
-// slower with the SAH tree; removed.)
-#ifndef RT_EXT_WIDE4
-#define RT_EXT_WIDE4 1         // 1: 4-wide quantised nodes (QNode4, two tree levels per step)  0: 2-wide QNode
-#endif
+// A pending ray (bit 31 of its sample index) is traversed twice: first through the light BVH, all hits, summing
+// bvh_mix_dist::pdf (raytracer.h:363-375; best_t stays +inf, so nothing is culled), then through the scene BVH for
+// the closest hit.  Both run in the same warp-synchronous loops; the lane goes from the one into the other inside
+// the pop step, without waiting for a refill section.
+//
+// Compile-time knobs (A/B-tested on the B200, DESIGN.md "k_extend"; defaults = the fastest measured).  Alternatives
+// that were measured and removed from the source: 2-wide 32-byte nodes, 64-byte full-precision nodes, node step before
+// the pop, two pops per step, one triangle per leaf iteration, light-to-scene switch in the refill section.
 #ifndef RT_EXT_SMEM_STACK
 #define RT_EXT_SMEM_STACK 16  // traversal-stack entries per thread kept in shared memory (0: all in local memory)
 #endif
 #ifndef RT_EXT_MIN_SEARCH
 #define RT_EXT_MIN_SEARCH 20  // leave the inner phase when fewer lanes than this still look for their first leaf
+#endif
+#ifndef RT_EXT_STEPS_PER_VOTE
+#define RT_EXT_STEPS_PER_VOTE 3  // 1 / 2 / 3 / 4 -> 103.4 / 100.4 / 99.3 / 100.4 ms of k_extend per 128 spp
+#endif
+#ifndef RT_EXT_MINB
+#define RT_EXT_MINB 8  // minimum resident CTAs per SM asked of the compiler: 8 = 64 registers, no spills
 #endif
 constexpr int32_t kLinkDone = static_cast<int32_t>(0x80000000u);  // nothing left to traverse
 constexpr int32_t kLinkPop = static_cast<int32_t>(0x80000001u);   // take the next entry from the stack
@@ -158,28 +166,8 @@ constexpr uint32_t kRayBlock = 128;
 // per launch, 31 % of the kernel's L1 sectors — profiles/r1_v2_k_extend_ncu_full.csv).
 constexpr int kSmemStack = RT_EXT_SMEM_STACK;
 constexpr int kMinSearching = RT_EXT_MIN_SEARCH;
-#ifndef RT_EXT_STEPS_PER_VOTE
-#define RT_EXT_STEPS_PER_VOTE 3  // 1 / 2 / 3 / 4 -> 103.4 / 100.4 / 99.3 / 100.4 ms of k_extend per 128 spp
-#endif
 constexpr int kStepsPerVote = RT_EXT_STEPS_PER_VOTE;
-#ifndef RT_EXT_LEAF_PAIR
-#define RT_EXT_LEAF_PAIR 1  // 1: the leaf phase intersects two triangles per iteration
-#endif
-#ifndef RT_EXT_STEP_ORDER
-#define RT_EXT_STEP_ORDER 1  // 0: node, pop, postpone   1: pop, node, postpone   2: pop, node, postpone, pop   3: pop, postpone, node, pop, postpone
-#endif
-#ifndef RT_EXT_INLINE_LMODE
-#define RT_EXT_INLINE_LMODE 1  // 1: a lane whose light-pdf traversal ends goes on into the scene BVH in the same step
-#endif
 constexpr uint32_t kNoRay = 0xFFFFFFFFu;
-#if RT_EXT_WIDE4
-#define RT_NODES(b) (b).qnodes4
-#define RT_ROOT(b) (b).root4
-#else
-#define RT_NODES(b) (b).qnodes
-#define RT_ROOT(b) (b).root
-#endif
-#define RT_ROOT_OF(b) RT_ROOT(b)
 
 // MUFU.RCP (1 ulp): one instruction instead of the IEEE division's Newton step + slow path
 __device__ __forceinline__ float rcp_rn(float x) {
@@ -187,20 +175,12 @@ __device__ __forceinline__ float rcp_rn(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
-__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 __device__ __forceinline__ bool link_is_leaf(int32_t link) { return link < 0 && link != kLinkDone && link != kLinkPop; }
 
-#ifndef RT_EXT_MINB
-#define RT_EXT_MINB 8  // minimum resident CTAs per SM asked of the compiler (0: let it choose); 8 = 64 registers, no spills
-#endif
-#if RT_EXT_MINB
-__global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB) k_extend(
-#else
-__global__ void __launch_bounds__(kExtendThreads) k_extend(
-#endif
-    DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce, uint32_t one) {
+__global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
+    k_extend(DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce,
+             uint32_t one) {
     // `one` = 0x3F800000, passed as an argument so that it is not an immediate (see qplane() in pt_core.cuh)
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t count = q.count[bounce];
@@ -213,68 +193,32 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
     // postponed far children: plane 0 = link, plane 1 = entry distance; `top` walks this thread's column
     constexpr int kPlane = (kSmemStack > 0 ? kSmemStack : 1) * kExtendThreads;
     __shared__ uint32_t s_stack[2 * kPlane];
-#if RT_EXT_WIDE4
     float2 overflow[96 - kSmemStack];  // up to three pushes per level of a tree half as deep as the binary one
-#else
-    float2 overflow[RT_STACK_SIZE - kSmemStack];
-#endif
     uint32_t *top = s_stack + threadIdx.x;  // slot of the NEXT push (valid while sp < kSmemStack)
     int sp = 0;
     int32_t link = kLinkDone;  // >= 0 inner node, kLinkPop / kLinkDone, otherwise a leaf (~first triangle)
     int32_t leaf = 0;          // postponed leaf link (always < 0) or 0 = none
-    uint32_t ray = kNoRay;
+    uint32_t ray = kNoRay;     // queue index; bit 31: pending (its light pdf is wanted)
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1), ood = mk3(0, 0, 0);
-    RaySwz sw = ray_swizzle(idir);
     float best_t = INFINITY, best_b = 0.0f, best_c = 0.0f;
     int32_t best_tri = -1;
-    // A pending ray (bit 31 of its sample index) is traversed twice: first through the light BVH, all hits, summing
-    // bvh_mix_dist::pdf (raytracer.h:363-375) into lsum (best_t stays +inf, so nothing is culled), then through the
-    // scene BVH for the closest hit.  Both run in the same warp-synchronous loops, so the light-pdf traversals get
-    // this kernel's lane occupancy and refill instead of k_shade's (7 of 32 lanes, 57 % of its instructions).
-    bool lmode = false;
-#if RT_EXT_INLINE_LMODE
+    bool lmode = false;   // the lane is in the light BVH
     bool leaf_l = false;  // the postponed leaf belongs to the light BVH
-    const int32_t scene_root = RT_ROOT_OF(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT_OF(bvh);
-#endif
     float lsum = 0.0f;
-#if RT_EXT_WIDE4
-    typedef QNode4 NodeT;
-#else
-    typedef QNode NodeT;
-#endif
-    const NodeT *node_base = RT_NODES(bvh);
-#if !RT_EXT_INLINE_LMODE
-    const DTri *tri_base = bvh.tris;
-#endif
+    const int32_t scene_root = bvh.root4 == RT_LINK_NONE ? kLinkDone : bvh.root4;
+    const QNode4 *node_base = bvh.qnodes4;
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
 
     for (;;) {
         // ---- retire finished rays, refill idle lanes ---------------------------------------------------
-        bool idle = link == kLinkDone && leaf == 0;
-#if RT_EXT_INLINE_LMODE
-        if (idle && ray != kNoRay) {  // bit 31 of `ray`: pending, its light pdf is wanted (0 without a light BVH)
+        const bool idle = link == kLinkDone && leaf == 0;
+        if (idle && ray != kNoRay) {
             const uint32_t r = ray & 0x7FFFFFFFu;
-            if (ray >> 31) q_store<0>(q.lpdf + r, lsum * inv_n_lights);
+            if (ray >> 31) q_store<0>(q.lpdf + r, lsum * inv_n_lights);  // 0 when the scene has no light BVH
             q_store<0>(q.hit + r, make_float4(best_t, best_b, best_c, __int_as_float(best_tri)));
             ray = kNoRay;
         }
-#else
-        if (idle && ray != kNoRay) {
-            if (lmode) {  // light pdf done: now the closest hit of the same ray
-                q.lpdf[ray] = lsum * inv_n_lights;
-                lmode = false;
-                node_base = RT_NODES(bvh);
-                tri_base = bvh.tris;
-                link = RT_ROOT(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT(bvh);
-                idle = link == kLinkDone;
-            }
-            if (idle) {
-                q.hit[ray] = make_float4(best_t, best_b, best_c, __int_as_float(best_tri));
-                ray = kNoRay;
-            }
-        }
-#endif
         const uint32_t m_idle = __ballot_sync(FULL, idle);
         if (m_idle) {
             if (pool_next == pool_end && !exhausted) {  // one atomicAdd per kRayBlock rays
@@ -299,30 +243,16 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                 d = mk3(d4.x, d4.y, d4.z);
                 idir = mk3(rcp_rn(d.x), rcp_rn(d.y), rcp_rn(d.z));
                 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-                sw = ray_swizzle(idir);
                 best_t = INFINITY;
                 best_b = best_c = 0.0f;
                 best_tri = -1;
                 sp = 0;
                 top = s_stack + threadIdx.x;
-                lmode = (__float_as_uint(d4.w) >> 31) != 0u && RT_ROOT(lbvh) != RT_LINK_NONE;
                 lsum = 0.0f;
-#if RT_EXT_INLINE_LMODE
+                lmode = (__float_as_uint(d4.w) >> 31) != 0u && lbvh.root4 != RT_LINK_NONE;
                 ray |= __float_as_uint(d4.w) & 0x80000000u;
-                node_base = lmode ? RT_NODES(lbvh) : RT_NODES(bvh);
-                link = lmode ? RT_ROOT(lbvh) : scene_root;  // a leaf root is postponed below
-#else
-                if (lmode) {
-                    node_base = RT_NODES(lbvh);
-                    tri_base = lbvh.tris;
-                    link = RT_ROOT(lbvh);
-                } else {
-                    if (__float_as_uint(d4.w) >> 31) q.lpdf[ray] = 0.0f;  // pending, but the scene has no light BVH
-                    node_base = RT_NODES(bvh);
-                    tri_base = bvh.tris;
-                    link = RT_ROOT(bvh) == RT_LINK_NONE ? kLinkDone : RT_ROOT(bvh);  // a leaf root is postponed below
-                }
-#endif
+                node_base = lmode ? lbvh.qnodes4 : bvh.qnodes4;
+                link = lmode ? lbvh.root4 : scene_root;  // a leaf root is postponed in the first step
             }
             pool_next += take;
             if (avail == 0 && m_idle == FULL) break;  // queue drained and nothing in flight
@@ -331,8 +261,8 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
 
         // ---- inner phase -------------------------------------------------------------------------------
         for (;;) {
-            // (3) phase vote, once per kStepsPerVote node steps: go on while at least kMinSearching lanes still look
-            //     for their first leaf (a lane that has nothing to do in a step simply idles through it)
+            // phase vote, once per kStepsPerVote steps: go on while at least kMinSearching lanes still look
+            // for their first leaf (a lane that has nothing to do in a step simply idles through it)
             const uint32_t m_search = __ballot_sync(FULL, leaf == 0 && link != kLinkDone);
             if (__popc(m_search) < kMinSearching) {
                 if (m_search == 0) break;
@@ -342,8 +272,34 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
             }
 #pragma unroll
             for (int step = 0; step < kStepsPerVote; ++step) {
-                auto node_step = [&]() {
-                // (4) at most one node step
+                // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
+                //     the lane pops again in the next step (bvh.h:221: far child only while best is farther).  An
+                //     empty stack ends the light traversal (on into the scene BVH; best_t is still +inf) or the ray.
+                {
+                    const bool need = link == kLinkPop;
+                    const bool has = need && sp > 0;
+                    int32_t l = kLinkDone;
+                    float t = -INFINITY;  // empty stack: t < best_t holds, link becomes l
+                    if (has) {
+                        --sp;
+                        if (kSmemStack > 0 && sp < kSmemStack) {
+                            top -= kExtendThreads;
+                            l = static_cast<int32_t>(top[0]);
+                            t = __uint_as_float(top[kPlane]);
+                        } else {
+                            const float2 e = overflow[sp - kSmemStack];
+                            l = __float_as_int(e.x);
+                            t = e.y;
+                        }
+                    }
+                    if (need && !has && lmode) {
+                        lmode = false;
+                        node_base = bvh.qnodes4;
+                        l = scene_root;
+                    }
+                    if (need) link = t < best_t ? l : kLinkPop;
+                }
+                // (2) at most one node step: four slab tests, nearest child next, the others onto the stack
                 if (link >= 0) {
                     auto push = [&](int32_t l, float t) {
                         if (kSmemStack > 0 && sp < kSmemStack) {
@@ -355,7 +311,6 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                         }
                         ++sp;
                     };
-#if RT_EXT_WIDE4
                     const char *np = reinterpret_cast<const char *>(node_base + link);
                     const f8 na = ld8(np), nb = ld8(np + 32);  // 64 B node: grid, 6 plane words, 4 links
                     const Node4Test nt = qnode4_test(f2u(na.a), f2u(na.b), f2u(na.c), f2u(na.d), f2u(na.e), f2u(na.f), f2u(na.g),
@@ -395,85 +350,27 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                         if (d1 < INFINITY) push(l1, d1);
                     }
                     link = d0 < INFINITY ? l0 : kLinkPop;
-#else
-                    const f8 nq = ld8(node_base + link);  // 32 B quantised node = one sector, one 256-bit load
-                    const NodeTest nt = qnode_test(f2u(nq.a), f2u(nq.b), f2u(nq.c), f2u(nq.d), f2u(nq.e), f2u(nq.f), idir, ood, sw,
-                                                   one, eps, best_t);
-                    const int32_t ll = static_cast<int32_t>(f2u(nq.g)), lr = static_cast<int32_t>(f2u(nq.h));
-                    // near child first; ties go left (bvh.h:216-219)
-                    const bool right_first = nt.hr && (!nt.hl || nt.dl > nt.dr);
-                    if (nt.hl && nt.hr) push(right_first ? ll : lr, right_first ? nt.dl : nt.dr);
-                    link = (nt.hl || nt.hr) ? (right_first ? lr : ll) : kLinkPop;
-#endif
                 }
-                };
-                auto pop_step = [&]() {
-                // (1) at most one pop: an entry whose subtree cannot hold a closer hit any more is dropped and
-                //     the lane pops again in the next iteration (bvh.h:221: far child only while best is farther)
-                {
-                    const bool need = link == kLinkPop;
-                    const bool has = need && sp > 0;
-                    int32_t l = kLinkDone;
-                    float t = -INFINITY;  // empty stack: t < best_t holds, link becomes kLinkDone
-                    if (has) {
-                        --sp;
-                        if (kSmemStack > 0 && sp < kSmemStack) {
-                            top -= kExtendThreads;
-                            l = static_cast<int32_t>(top[0]);
-                            t = __uint_as_float(top[kPlane]);
-                        } else {
-                            const float2 e = overflow[sp - kSmemStack];
-                            l = __float_as_int(e.x);
-                            t = e.y;
-                        }
-                    }
-#if RT_EXT_INLINE_LMODE
-                    if (need && !has && lmode) {  // light BVH exhausted: on into the scene BVH (best_t is still +inf)
-                        lmode = false;
-                        node_base = RT_NODES(bvh);
-                        l = scene_root;
-                    }
-#endif
-                    if (need) link = t < best_t ? l : kLinkPop;
-                }
-                };
-                auto postpone_step = [&]() {
-                // (2) postpone the first leaf and keep descending; a lane that meets a second one waits
+                // (3) postpone the first leaf and keep descending (the next step pops); a lane that meets a second
+                //     one waits with it
                 if (leaf == 0 && link_is_leaf(link)) {
                     leaf = link;
-#if RT_EXT_INLINE_LMODE
                     leaf_l = lmode;
-#endif
                     link = kLinkPop;
                 }
-                };
-#if RT_EXT_STEP_ORDER == 0
-                node_step(); pop_step(); postpone_step();
-#elif RT_EXT_STEP_ORDER == 1
-                pop_step(); node_step(); postpone_step();
-#elif RT_EXT_STEP_ORDER == 2
-                pop_step(); node_step(); postpone_step(); pop_step();
-#else
-                pop_step(); postpone_step(); node_step(); pop_step(); postpone_step();
-#endif
             }
         }
 
-        // ---- leaf phase: all postponed leaves, triangle by triangle ------------------------------------
+        // ---- leaf phase: all postponed leaves, two triangles per iteration -------------------------------
         {
             uint32_t k = static_cast<uint32_t>(~leaf);
             bool more = leaf != 0;
             while (__any_sync(FULL, more)) {
                 if (more) {
-#if RT_EXT_INLINE_LMODE
                     const bool lt = leaf_l;
                     const char *p = reinterpret_cast<const char *>((lt ? lbvh.tris : bvh.tris) + k);
-#else
-                    const bool lt = lmode;
-                    const char *p = reinterpret_cast<const char *>(tri_base + k);
-#endif
                     // intersect_ray_triangle, bvh.h:36-65 (same expression as tri_test() in pt_core.cuh with
-                    // a correctly rounded reciprocal instead of the division)
+                    // the reciprocal instead of the division)
                     auto tri = [&](const f8 &ta, const f4 &t2, uint32_t kk) {
                         const f3 e1 = mk3(ta.e, ta.f, ta.g), e2 = mk3(t2.x, t2.y, t2.z);
                         const f3 n = cross(e1, e2);
@@ -497,24 +394,17 @@ __global__ void __launch_bounds__(kExtendThreads) k_extend(
                         }
                         return (f2u(ta.d) & RT_LAST_BIT) != 0u;
                     };
-#if RT_EXT_LEAF_PAIR
-                    // two triangles per iteration (the second one speculatively loaded: the array ends with a null
-                    // triangle): the scene's leaves mostly hold a quad, and the load latency is paid once per leaf
+                    // the second triangle is loaded speculatively (the array ends with a null triangle): the scene's
+                    // leaves mostly hold a quad, and the load latency is paid once per leaf
                     const f8 ta = ld8(p), tb = ld8(p + 64);
                     const f4 ta2 = ld4(p + 32), tb2 = ld4(p + 96);
                     bool last = tri(ta, ta2, k);
                     if (!last) last = tri(tb, tb2, k + 1);
                     more = !last;
                     k += 2;
-#else
-                    const f8 ta = ld8(p);
-                    const f4 t2 = ld4(p + 32);
-                    more = !tri(ta, t2, k);
-                    ++k;
-#endif
                 }
             }
-            leaf = 0;  // a lane that waited with a second leaf postpones it in step (2) of the next inner phase
+            leaf = 0;  // a lane that waited with a second leaf postpones it in step (3) of the next inner phase
         }
     }
 }

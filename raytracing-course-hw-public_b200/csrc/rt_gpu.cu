@@ -117,8 +117,7 @@ struct DeviceState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
     // scene
-    DevBuf<QNode> qnodes, lqnodes;  // scene BVH and light BVH, quantised (both traversed by k_extend)
-    DevBuf<QNode4> qnodes4, lqnodes4;  // their 4-wide collapses
+    DevBuf<QNode4> qnodes4, lqnodes4;  // scene BVH and light BVH, 4-wide quantised (both traversed by k_extend)
     DevBuf<QNode8> qnodes8, lqnodes8;  // 8-wide (RT_EXT_WIDE8 builds)
     DevBuf<DTri> tris, ltris, lsample;
     DevBuf<DAttr> attrs;
@@ -178,12 +177,9 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
 #if RT_EXT_WIDE8  // only the node format the traversal kernel was built for goes to the device
     if (int rc = d.qnodes8.upload(p.scene.qnodes8, d.stream)) return rc;
     if (int rc = d.lqnodes8.upload(p.light.qnodes8, d.stream)) return rc;
-#elif RT_EXT_WIDE4
+#else
     if (int rc = d.qnodes4.upload(p.scene.qnodes4, d.stream)) return rc;
     if (int rc = d.lqnodes4.upload(p.light.qnodes4, d.stream)) return rc;
-#else
-    if (int rc = d.qnodes.upload(p.scene.qnodes, d.stream)) return rc;
-    if (int rc = d.lqnodes.upload(p.light.qnodes, d.stream)) return rc;
 #endif
     if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
     if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
@@ -198,14 +194,14 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     if (int rc = d.lut.upload(lut, d.stream)) return rc;
     rt::fill_scene_constants(sc, p, d.scene);
     d.scene.scene.nodes = nullptr;  // the device traverses the quantised copies only
-    d.scene.scene.qnodes = d.qnodes.p;
+    d.scene.scene.qnodes = nullptr;  // the 2-wide form exists on the host only (tests)
     d.scene.scene.qnodes4 = d.qnodes4.p;
     d.scene.light.qnodes4 = d.lqnodes4.p;
     d.scene.scene.qnodes8 = d.qnodes8.p;
     d.scene.light.qnodes8 = d.lqnodes8.p;
     d.scene.scene.tris = d.tris.p;
     d.scene.light.nodes = nullptr;
-    d.scene.light.qnodes = d.lqnodes.p;
+    d.scene.light.qnodes = nullptr;
     d.scene.light.tris = d.ltris.p;
     d.scene.light_sample = d.lsample.p;
     d.scene.attrs = d.attrs.p;
@@ -484,7 +480,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
         cudaStreamSynchronize(d.stream);
-        d.qnodes.release(); d.lqnodes.release(); d.qnodes4.release(); d.lqnodes4.release(); d.qnodes8.release(); d.lqnodes8.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
+        d.qnodes4.release(); d.lqnodes4.release(); d.qnodes8.release(); d.lqnodes8.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }
@@ -535,7 +531,7 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     struct ResetTimes {
         ~ResetTimes() { rt::pack_times() = nullptr; }
     } reset_times;
-    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : RT_EXT_WIDE4 ? rt::RT_PACK_Q4 : rt::RT_PACK_Q2)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : rt::RT_PACK_Q4)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
     const auto t_pack1 = std::chrono::steady_clock::now();
     for (auto &d : ctx->devs)
         if (int rc = upload_to_device(*d, *scene, packed)) return rc;

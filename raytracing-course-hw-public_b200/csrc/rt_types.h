@@ -7,12 +7,12 @@
 //   DNode  64 B  one per INNER node of the binary tree: both children's boxes (full precision) + child
 //                links.  The reference tests both child boxes at the parent (bvh.h:205-212), so one
 //                fetch replaces two 40 B node fetches.  Host-side intermediate (and host checks) only.
-//   QNode  32 B  the same inner node with both child boxes quantised to 8 bits per plane on a per-node
+//   QNode  32 B  (host checks only; the device traversed it before QNode4) the same inner node with both child boxes quantised to 8 bits per plane on a per-node
 //                power-of-two grid (conservative: the decoded box always contains the exact one): one
 //                node visit is ONE 32-byte sector.  Divergent addresses cost the L1 data pipe one
 //                sector per cycle, so bytes per node visit matter ("k_extend").
 //   QNode4 64 B  two binary levels collapsed: the 2..4 grandchildren's boxes on one grid + 4 links;
-//                what k_extend traverses by default (RT_EXT_WIDE4).
+//                what k_extend traverses.
 //   DTri   64 B  triangle in BVH order: a, (b-a), (c-a) + scene.objects id + end-of-leaf flag, padded to
 //                64 B so that it is two 256-bit loads (LDG.E.256 on sm_100a) inside one 128 B line.
 //   DAttr  64 B  per-vertex normals + uv + material id, BVH order (read once per shade).
