@@ -127,6 +127,153 @@ int32_t collapse(const std::vector<DNode> &nodes, int32_t link, int width, std::
     return idx;
 }
 
+
+// ---- cost-optimal 8-wide collapse (Ylitie et al. 2017, sec. 4.1, without leaf merging): minimises the summed box
+// area of the wide nodes.  C[n][i-1] = cost of representing the binary subtree n by at most i children of its parent.
+struct DpCollapse {
+    const std::vector<DNode> &nodes;
+    std::vector<float> C;       // 8 per inner node
+    std::vector<uint8_t> split; // [n][i-1]: slots given to the left subtree when n is distributed over i slots (0: take C[n][i-2])
+    std::vector<float> area_of; // box area of each inner node (from its parent's record); root: 0
+    int W;
+    DpCollapse(const std::vector<DNode> &nd, int width = 8) : nodes(nd), C(nd.size() * 8, 0.0f), split(nd.size() * 8, 0), area_of(nd.size(), 0.0f), W(width) {}
+    float cost(int32_t link, int i) const { return link < 0 ? 0.0f : C[(size_t)link * 8 + (i - 1)]; }
+    void solve(int32_t n) {
+        if (n < 0) return;
+        Item k[2];
+        kids(nodes[n], k);
+        for (int c = 0; c < 2; ++c)
+            if (k[c].link >= 0) {
+                area_of[k[c].link] = area(k[c]);
+                solve(k[c].link);
+            }
+        // dist[j] = best split of j slots (j = 2..8) over the two subtrees
+        float dist[9];
+        uint8_t arg[9];
+        for (int j = 2; j <= W; ++j) {
+            dist[j] = 1e30f;
+            arg[j] = 1;
+            for (int a = 1; a < j; ++a) {
+                const float v = cost(k[0].link, std::min(a, W - 1)) + cost(k[1].link, std::min(j - a, W - 1));
+                if (v < dist[j]) dist[j] = v, arg[j] = (uint8_t)a;
+            }
+        }
+        float *c = &C[(size_t)n * 8];
+        uint8_t *sp = &split[(size_t)n * 8];
+        c[0] = area_of[n] + dist[W];  // n is a wide node of its own
+        sp[0] = arg[W];
+        for (int i = 2; i <= W; ++i) {
+            if (dist[i] < c[i - 2]) c[i - 1] = dist[i], sp[i - 1] = arg[i];
+            else c[i - 1] = c[i - 2], sp[i - 1] = 0;
+        }
+    }
+    // children of the wide node that n's subtree contributes when it may use i slots
+    void expand(int32_t link, const Item &self, int i, std::vector<Item> &out) const {
+        if (link < 0) {
+            out.push_back(self);
+            return;
+        }
+        while (i > 1 && split[(size_t)link * 8 + (i - 1)] == 0) --i;
+        if (i == 1) {
+            out.push_back(self);  // stays an inner child: its own wide node
+            return;
+        }
+        const int a = split[(size_t)link * 8 + (i - 1)];
+        Item k[2];
+        kids(nodes[link], k);
+        expand(k[0].link, k[0], std::min(a, W - 1), out);
+        expand(k[1].link, k[1], std::min(i - a, W - 1), out);
+    }
+};
+int32_t collapse_dp(const DpCollapse &dp, int32_t link, std::vector<WNode> &out);
+
+int32_t collapse_dp(const DpCollapse &dp, int32_t link, std::vector<WNode> &out) {
+    if (link < 0) return link;
+    const std::vector<DNode> &nodes = dp.nodes;
+    const int width = dp.W;
+    std::vector<Item> items;
+    Item k[2];
+    kids(nodes[link], k);
+    const int a = dp.split[(size_t)link * 8 + 0];
+    dp.expand(k[0].link, k[0], std::min(a, width - 1), items);
+    dp.expand(k[1].link, k[1], std::min(width - a, width - 1), items);
+    Item it[8];
+    const int n = (int)items.size();
+    for (int i = 0; i < n; ++i) it[i] = items[i];
+    // slot assignment: greedy on dot(child centre - node centre, slot direction); slot s bit k set = positive side
+    float c[3] = {0, 0, 0}, lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = it[0].lo[k];
+        hi[k] = it[0].hi[k];
+        for (int i = 1; i < n; ++i) lo[k] = std::min(lo[k], it[i].lo[k]), hi[k] = std::max(hi[k], it[i].hi[k]);
+        c[k] = 0.5f * (lo[k] + hi[k]);
+    }
+    const int slots = width;
+    // 4 slots: the two axes along which the child centres spread most
+    int ax0 = 0, ax1 = 1;
+    {
+        float spread[3];
+        for (int k = 0; k < 3; ++k) {
+            float mn = 1e30f, mx = -1e30f;
+            for (int i = 0; i < n; ++i) {
+                const float cc = 0.5f * (it[i].lo[k] + it[i].hi[k]);
+                mn = std::min(mn, cc), mx = std::max(mx, cc);
+            }
+            spread[k] = mx - mn;
+        }
+        int order[3] = {0, 1, 2};
+        std::sort(order, order + 3, [&](int a, int b) { return spread[a] > spread[b]; });
+        ax0 = order[0];
+        ax1 = order[1];
+    }
+    int slot_of[8];
+    bool used[8] = {false}, done[8] = {false};
+    for (int round = 0; round < n; ++round) {
+        float bestv = -1e30f;
+        int bi = -1, bs = -1;
+        for (int i = 0; i < n; ++i) {
+            if (done[i]) continue;
+            for (int s = 0; s < slots; ++s) {
+                if (used[s]) continue;
+                float v = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const float cc = 0.5f * (it[i].lo[k] + it[i].hi[k]) - c[k];
+                    int bit;
+                    if (slots == 8) bit = (s >> k) & 1;
+                    else if (k == ax0) bit = s & 1;
+                    else if (k == ax1) bit = (s >> 1) & 1;
+                    else continue;
+                    v += bit ? cc : -cc;
+                }
+                if (v > bestv) bestv = v, bi = i, bs = s;
+            }
+        }
+        done[bi] = true;
+        used[bs] = true;
+        slot_of[bi] = bs;
+    }
+    const int32_t idx = (int32_t)out.size();
+    out.emplace_back();
+    WNode w;
+    w.n = slots;
+    w.ax0 = ax0;
+    w.ax1 = ax1;
+    for (int s = 0; s < 8; ++s) w.ch[s].link = RT_LINK_NONE;
+    for (int i = 0; i < n; ++i) {
+        WChild &cdst = w.ch[slot_of[i]];
+        std::memcpy(cdst.lo, it[i].lo, 12);
+        std::memcpy(cdst.hi, it[i].hi, 12);
+        cdst.link = it[i].link;
+    }
+    out[idx] = w;
+    for (int s = 0; s < slots; ++s)
+        if (out[idx].ch[s].link != RT_LINK_NONE && out[idx].ch[s].link >= 0) {
+            const int32_t l = collapse_dp(dp, out[idx].ch[s].link, out);
+            out[idx].ch[s].link = l;
+        }
+    return idx;
+}
+
 struct Cnt {
     uint64_t rays = 0, nodes = 0, tris = 0, pops = 0, culled = 0, leaves = 0, pushes = 0;
 };
@@ -331,7 +478,16 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     d.texels = p.texels.data();
     std::vector<WNode> W4, W8;
     const int32_t r4 = collapse(p.scene.nodes, p.scene.root, 4, W4), r8 = collapse(p.scene.nodes, p.scene.root, 8, W8);
-    std::printf("binary inner nodes %zu, 4-wide %zu, 8-wide %zu\n", p.scene.nodes.size(), W4.size(), W8.size());
+    std::vector<WNode> W8d;
+    DpCollapse dp(p.scene.nodes);
+    dp.solve(p.scene.root);
+    const int32_t r8d = collapse_dp(dp, p.scene.root, W8d);
+    std::vector<WNode> W4d;
+    DpCollapse dp4(p.scene.nodes, 4);
+    dp4.solve(p.scene.root);
+    const int32_t r4d = collapse_dp(dp4, p.scene.root, W4d);
+    std::printf("binary inner nodes %zu, 4-wide greedy %zu, cost-optimal %zu; 8-wide greedy %zu, cost-optimal %zu\n", p.scene.nodes.size(),
+                W4.size(), W4d.size(), W8.size(), W8d.size());
     Camera c;
     c.pos = mk3(d.cam_pos[0], d.cam_pos[1], d.cam_pos[2]);
     c.right = mk3(d.cam_right[0], d.cam_right[1], d.cam_right[2]);
@@ -341,7 +497,7 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     c.tan_half_y = tanf(atanf(tanf(d.fov_x / 2) * (float)h / (float)w));
     c.inv_w2 = 2.0f / (float)w;
     c.inv_h2 = 2.0f / (float)h;
-    Cnt a4, b4, b4d, a8, b8, b8d, q4;
+    Cnt a4, b4, b4d, a8, b8, b8d, q4, b8o, a4o;
     uint64_t mism = 0;
     for (uint32_t pix = 0; pix < w * h; ++pix)
         for (uint32_t s = 0; s < spp; ++s) {
@@ -361,6 +517,8 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
                 trav_sorted(W8, r8, 8, d.scene, o, dir, d.eps, a8);
                 const Hit h3 = trav_oct(W8, r8, 8, d.scene, o, dir, d.eps, b8, false);
                 trav_oct(W8, r8, 8, d.scene, o, dir, d.eps, b8d, true);
+                trav_oct(W8d, r8d, 8, d.scene, o, dir, d.eps, b8o, false);
+                trav_sorted(W4d, r4d, 4, d.scene, o, dir, d.eps, a4o);
                 mism += (h1.tri != hit.tri) + (h2.tri != hit.tri) + (h3.tri != hit.tri);
                 uint32_t lr = 0;
                 if (!shade_bounce(d, p.gamma_lut, key, b, b + 1 == d.ray_depth, hit, o, dir, thr, rad, lr)) break;
@@ -374,5 +532,7 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     report("A8 sorted + distance stack", a8);
     report("B8 octant order, mask stack", b8);
     report("B8 distance order, mask stack", b8d);
+    report("B8 cost-optimal collapse, octant", b8o);
+    report("A4 cost-optimal collapse, sorted", a4o);
     return 0;
 }
