@@ -451,18 +451,23 @@ RT_HD Grid3 qgrid(uint32_t ox, uint32_t oy, uint32_t oz, f3 idir, f3 ood) {
     g.az = u2f((oz << 23) + 0x08000000u) * idir.z, g.bz = fmaf(u2f(oz), idir.z, -ood.z) - g.az;
     return g;
 }
+// slab test of child C of a plane group: entry (max of the near planes, eps) <= exit (min of the far planes, best_t)
+template <int C> RT_HD bool q4_hit(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, const Grid3 &g, uint32_t one,
+                                   float eps, float best_t) {
+    const float entry = fmaxf(fmaxf(fmaxf(fmaf(qplane<C>(nx, one), g.ax, g.bx), fmaf(qplane<C>(ny, one), g.ay, g.by)),
+                                    fmaf(qplane<C>(nz, one), g.az, g.bz)), eps);
+    const float exit_ = fminf(fminf(fminf(fmaf(qplane<C>(fx, one), g.ax, g.bx), fmaf(qplane<C>(fy, one), g.ay, g.by)),
+                                    fmaf(qplane<C>(fz, one), g.az, g.bz)), best_t);
+    return entry <= exit_;
+}
 // hit bits of the four children of one plane group (lo x/y/z, hi x/y/z words)
 RT_HD uint32_t q8_group_hits(uint32_t lox, uint32_t loy, uint32_t loz, uint32_t hix, uint32_t hiy, uint32_t hiz, const Grid3 &g, bool px,
                              bool py, bool pz, uint32_t one, float eps, float best_t) {
     const uint32_t nx = px ? lox : hix, fx = px ? hix : lox;
     const uint32_t ny = py ? loy : hiy, fy = py ? hiy : loy;
     const uint32_t nz = pz ? loz : hiz, fz = pz ? hiz : loz;
-    uint32_t m = 0;
-    m |= q4_entry<0>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 1u : 0u;
-    m |= q4_entry<1>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 2u : 0u;
-    m |= q4_entry<2>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 4u : 0u;
-    m |= q4_entry<3>(nx, ny, nz, fx, fy, fz, g.ax, g.bx, g.ay, g.by, g.az, g.bz, one, eps, best_t) < INFINITY ? 8u : 0u;
-    return m;
+    return (q4_hit<0>(nx, ny, nz, fx, fy, fz, g, one, eps, best_t) ? 1u : 0u) | (q4_hit<1>(nx, ny, nz, fx, fy, fz, g, one, eps, best_t) ? 2u : 0u) |
+           (q4_hit<2>(nx, ny, nz, fx, fy, fz, g, one, eps, best_t) ? 4u : 0u) | (q4_hit<3>(nx, ny, nz, fx, fy, fz, g, one, eps, best_t) ? 8u : 0u);
 }
 // triangle position of the leaf child in slot s: tri_base + the counts (2 bits per slot) of the lower slots
 RT_HD uint32_t leaf8_offset(uint32_t counts, uint32_t s) {

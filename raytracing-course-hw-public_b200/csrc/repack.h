@@ -309,6 +309,9 @@ inline int quantize_nodes4(const std::vector<Node4Boxes> &boxes, std::vector<QNo
 
 // ---- 8-wide collapse (QNode8) ---------------------------------------------------------------------------------
 constexpr uint32_t kLeaf8 = 3;  // triangles per leaf child (2 count bits per slot)
+#ifndef RT_COLLAPSE8_OPTIMAL
+#define RT_COLLAPSE8_OPTIMAL 1  // 1: cost-optimal collapse (6.0 of 8 slots filled on the bench scene)  0: greedy (4.5)
+#endif
 struct Item8 {
     int32_t link;     // >= 0: inner node of the binary tree; < 0: the triangle range [tb, te) (BVH-order positions)
     uint32_t tb, te;
@@ -381,30 +384,102 @@ struct Collapse8 {
             two[1] = range_item(mid, it.te);
         }
     }
+    // Cost-optimal collapse (Ylitie, Karras & Laine 2017, sec. 4.1, without leaf merging): c[i-1] = the least summed box
+    // area of the wide nodes below an item when it may occupy at most i slots of its parent; s[i-1] = slots given to
+    // its first half (0: same as with i-1 slots; i == 1: the item is a wide node of its own and s[0] splits its 8 slots).
+    struct Table {
+        float c[8];
+        uint8_t s[8];
+    };
+    std::vector<Table> memo;
+    std::vector<uint8_t> memo_done;
+    Table table_of(const Item8 &item) {  // item.openable()
+        if (item.link >= 0 && memo_done[item.link]) return memo[item.link];
+        Item8 two[2];
+        open(item, two);
+        Table t[2];
+        bool op[2];
+        for (int c = 0; c < 2; ++c) {
+            op[c] = two[c].openable();
+            if (op[c]) t[c] = table_of(two[c]);
+        }
+        float dist[9];
+        uint8_t arg[9];
+        for (int j = 2; j <= 8; ++j) {
+            dist[j] = std::numeric_limits<float>::infinity();
+            arg[j] = 1;
+            for (int a = 1; a < j; ++a) {
+                const float v = (op[0] ? t[0].c[std::min(a, 7) - 1] : 0.0f) + (op[1] ? t[1].c[std::min(j - a, 7) - 1] : 0.0f);
+                if (v < dist[j]) {
+                    dist[j] = v;
+                    arg[j] = static_cast<uint8_t>(a);
+                }
+            }
+        }
+        Table r;
+        r.c[0] = box_area(item) + dist[8];
+        r.s[0] = arg[8];
+        for (int i = 2; i <= 8; ++i) {
+            if (dist[i] < r.c[i - 2]) {
+                r.c[i - 1] = dist[i];
+                r.s[i - 1] = arg[i];
+            } else {
+                r.c[i - 1] = r.c[i - 2];
+                r.s[i - 1] = 0;
+            }
+        }
+        if (item.link >= 0) {
+            memo[item.link] = r;
+            memo_done[item.link] = 1;
+        }
+        return r;
+    }
+    void expand(const Item8 &item, int slots, Item8 *out_items, int &n) {
+        if (!item.openable()) {
+            out_items[n++] = item;
+            return;
+        }
+        const Table t = table_of(item);
+        while (slots > 1 && t.s[slots - 1] == 0) --slots;
+        if (slots == 1) {
+            out_items[n++] = item;  // stays an inner child: a wide node of its own
+            return;
+        }
+        const int a = t.s[slots - 1];
+        Item8 two[2];
+        open(item, two);
+        expand(two[0], std::min(a, 7), out_items, n);
+        expand(two[1], std::min(slots - a, 7), out_items, n);
+    }
     // builds wide node `idx` (already allocated) from `self`
     void build(const Item8 &self, uint32_t idx) {
         Item8 it[8];
-        int n;
-        if (self.openable()) {
+        int n = 0;
+        if (!self.openable()) {
+            it[n++] = self;
+        } else if (RT_COLLAPSE8_OPTIMAL) {
+            const Table t = table_of(self);
+            Item8 two[2];
+            open(self, two);
+            expand(two[0], std::min<int>(t.s[0], 7), it, n);
+            expand(two[1], std::min<int>(8 - t.s[0], 7), it, n);
+        } else {
             open(self, it);
             n = 2;
-        } else {
-            it[0] = self;
-            n = 1;
-        }
-        while (n < 8) {  // open the child with the largest box until eight children or nothing left to open
-            int best = -1;
-            float best_area = -1.0f;
-            for (int i = 0; i < n; ++i)
-                if (it[i].openable() && box_area(it[i]) > best_area) {
-                    best_area = box_area(it[i]);
-                    best = i;
-                }
-            if (best < 0) break;
-            Item8 two[2];
-            open(it[best], two);
-            it[best] = two[0];
-            it[n++] = two[1];
+            while (n < 8) {  // greedy: open the child with the largest box until eight children or nothing left to open
+                int best = -1;
+                float best_area = -1.0f;
+                for (int i = 0; i < n; ++i)
+                    if (it[i].openable() && box_area(it[i]) > best_area) {
+                        best_area = box_area(it[i]);
+                        best = i;
+                    }
+                if (best < 0) break;
+                Item8 two[2];
+                open(it[best], two);
+                it[best] = two[0];
+                it[n++] = two[1];
+            }
         }
         // slots by octant: greedily the (child, slot) pair with the largest dot(child centre - node centre, slot direction)
         float c[3];
@@ -550,7 +625,9 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
         std::vector<uint32_t> perm, last;
         perm.reserve(src.n_objects);
         out.qnodes8.reserve(out.nodes.size() / 3 + 2);
-        detail::Collapse8 cl{out.nodes, out.tris, out.qnodes8, boxes, perm, last};
+        detail::Collapse8 cl{out.nodes, out.tris, out.qnodes8, boxes, perm, last, {}, {}};
+        cl.memo.resize(out.nodes.size());
+        cl.memo_done.assign(out.nodes.size(), 0);
         // root item: the box is not needed (the root's own box is never tested, bvh.h:170-180)
         const float z[3] = {0.0f, 0.0f, 0.0f};
         detail::Item8 root = cl.link_item(out.root, z, z);
