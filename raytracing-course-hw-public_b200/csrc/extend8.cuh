@@ -10,8 +10,9 @@
 //     one 3-stage bit permutation of the mask per step instead of a distance sort of the children;
 //   * the stack holds GROUPS (first inner child, permuted hit mask | imask) — at most one push per step — and no
 //     distances: a stale entry is culled when its own children are tested against the current best_t.  On the bench
-//     scene that is 10.9 node steps per path-traced ray against 16.0 of the 4-wide sorted traversal
-//     (tools/wide_study.cpp) at about the same instructions per step;
+//     scene that is 10.1 node steps per path-traced ray against 16.0 of the 4-wide sorted traversal
+//     (tools/wide_study.cpp), but ~300 instead of 216 instructions per step: measured 88 ms of k_extend8 against
+//     83.7 ms of k_extend per 128 spp on the B200, which is why this build is optional;
 //   * leaf children are (first triangle, hit slots | triangle counts) groups; one group per lane can be postponed, a
 //     lane that meets a second one parks it as its current group and waits for the leaf phase.
 // Group encoding (x, y):  y >= 2^24: node group, bits 24..31 = hit children by PRIORITY (bit p = slot p ^ octinv), bits
