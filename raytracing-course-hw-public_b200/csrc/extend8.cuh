@@ -52,10 +52,9 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT8_MINB)
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     constexpr int kS = RT_EXT8_SMEM_STACK;
-    constexpr int kPlane = kS * kExtendThreads;
-    __shared__ uint32_t s_stack[2 * kPlane];
+    __shared__ uint2 s_stack[kS * kExtendThreads];  // [entry][thread]: one 64-bit access per group
     uint2 overflow[2 * RT_STACK_SIZE - kS];  // at most two pushes per level of a tree no deeper than the binary one
-    uint32_t *top = s_stack + threadIdx.x;  // slot of the next push (valid while sp < kS)
+    uint2 *top = s_stack + threadIdx.x;  // slot of the next push (valid while sp < kS)
     int sp = 0;
     uint32_t gx = kDone8, gy = 0;  // current group
     uint32_t tx = 0, ty = 0;       // postponed triangle group
@@ -73,8 +72,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT8_MINB)
 
     auto push = [&](uint32_t x, uint32_t y) {
         if (sp < kS) {
-            top[0] = x;
-            top[kPlane] = y;
+            top[0] = make_uint2(x, y);
             top += kExtendThreads;
         } else {
             overflow[sp - kS] = make_uint2(x, y);
@@ -151,8 +149,9 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT8_MINB)
                         --sp;
                         if (sp < kS) {
                             top -= kExtendThreads;
-                            gx = top[0];
-                            gy = top[kPlane];
+                            const uint2 e = top[0];
+                            gx = e.x;
+                            gy = e.y;
                         } else {
                             const uint2 e = overflow[sp - kS];
                             gx = e.x;
