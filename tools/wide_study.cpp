@@ -398,7 +398,7 @@ Hit trav_oct(const std::vector<WNode> &W, int32_t root, int width, const DBvh &b
 }
 
 // scheme A on the same wide nodes: sorted by distance, (link, t) stack, cull at pop
-Hit trav_sorted(const std::vector<WNode> &W, int32_t root, int width, const DBvh &bvh, f3 o, f3 d, float eps, Cnt &c) {
+Hit trav_sorted(const std::vector<WNode> &W, int32_t root, int width, const DBvh &bvh, f3 o, f3 d, float eps, Cnt &c, int mode = 0) {
     Hit best;
     best.t = INFINITY;
     best.b = best.c = 0;
@@ -422,8 +422,23 @@ Hit trav_sorted(const std::vector<WNode> &W, int32_t root, int width, const DBvh
                 const float t = slab(ch.lo[0], ch.lo[1], ch.lo[2], ch.hi[0], ch.hi[1], ch.hi[2], o, idir, eps);
                 if (t >= 0.0f && t < best.t) dist[m] = t, ls[m++] = ch.link;
             }
-            for (int i = 1; i < m; ++i)
-                for (int j = i; j > 0 && dist[j] < dist[j - 1]; --j) std::swap(dist[j], dist[j - 1]), std::swap(ls[j], ls[j - 1]);
+            if (mode == 0) {  // full sort
+                for (int i = 1; i < m; ++i)
+                    for (int j = i; j > 0 && dist[j] < dist[j - 1]; --j) std::swap(dist[j], dist[j - 1]), std::swap(ls[j], ls[j - 1]);
+            } else if (m > 1) {  // only the nearest child is found (three compare-exchanges: (0,1) (2,3) (0,2)); the rest keeps its order
+                int best = 0;
+                for (int i = 1; i < m; ++i)
+                    if (dist[i] < dist[best]) best = i;
+                std::swap(dist[0], dist[best]);
+                std::swap(ls[0], ls[best]);
+                if (mode == 2 && m > 2) {  // ... plus the farthest to the bottom of the pushes
+                    int far = 1;
+                    for (int i = 2; i < m; ++i)
+                        if (dist[i] > dist[far]) far = i;
+                    std::swap(dist[m - 1], dist[far]);
+                    std::swap(ls[m - 1], ls[far]);
+                }
+            }
             for (int i = m - 1; i >= 1; --i) sl[sp] = ls[i], stt[sp++] = dist[i], ++c.pushes;
             if (m > 0) {
                 link = ls[0];
@@ -497,7 +512,7 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     c.tan_half_y = tanf(atanf(tanf(d.fov_x / 2) * (float)h / (float)w));
     c.inv_w2 = 2.0f / (float)w;
     c.inv_h2 = 2.0f / (float)h;
-    Cnt a4, b4, b4d, a8, b8, b8d, q4, b8o, a4o;
+    Cnt a4, b4, b4d, a8, b8, b8d, q4, b8o, a4o, a4m, a4m2;
     uint64_t mism = 0;
     for (uint32_t pix = 0; pix < w * h; ++pix)
         for (uint32_t s = 0; s < spp; ++s) {
@@ -519,6 +534,8 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
                 trav_oct(W8, r8, 8, d.scene, o, dir, d.eps, b8d, true);
                 trav_oct(W8d, r8d, 8, d.scene, o, dir, d.eps, b8o, false);
                 trav_sorted(W4d, r4d, 4, d.scene, o, dir, d.eps, a4o);
+                trav_sorted(W4, r4, 4, d.scene, o, dir, d.eps, a4m, 1);
+                trav_sorted(W4, r4, 4, d.scene, o, dir, d.eps, a4m2, 2);
                 mism += (h1.tri != hit.tri) + (h2.tri != hit.tri) + (h3.tri != hit.tri);
                 uint32_t lr = 0;
                 if (!shade_bounce(d, p.gamma_lut, key, b, b + 1 == d.ray_depth, hit, o, dir, thr, rad, lr)) break;
@@ -534,5 +551,7 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     report("B8 distance order, mask stack", b8d);
     report("B8 cost-optimal collapse, octant", b8o);
     report("A4 cost-optimal collapse, sorted", a4o);
+    report("A4 nearest first, rest unsorted", a4m);
+    report("A4 nearest first, farthest last", a4m2);
     return 0;
 }
