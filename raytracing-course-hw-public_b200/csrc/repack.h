@@ -307,6 +307,144 @@ inline int quantize_nodes4(const std::vector<Node4Boxes> &boxes, std::vector<QNo
     return rc;
 }
 
+// ---- 4-wide collapse straight from a tree of the library's own builder, sub-trees in parallel ------------------------
+// sah_build.h's trees are well formed (every inner node has two non-empty children, a leaf holds [obj_begin, obj_end)),
+// so the binary DNode array and its serial construction (pack_node) are skipped on the upload path: the wide nodes of
+// the top three levels are made serially, the sub-trees below them by one task each into private arrays that are
+// appended afterwards (inner links shifted by the task's base index).
+struct Built4 {
+    const rt_bvh_desc &src;
+    std::vector<DTri> &tris;
+    int32_t null_leaf;
+    // link of binary node i for the collapse: >= 0 = i itself (inner), < 0 = ~first triangle (leaf; its last triangle is marked)
+    int32_t link_of(uint32_t i) const {
+        const rt_bvh_node &nd = src.nodes[i];
+        if (nd.left_child == RT_NO_CHILD && nd.right_child == RT_NO_CHILD) {
+            tris[nd.obj_end - 1].id_last |= RT_LAST_BIT;
+            return ~static_cast<int32_t>(nd.obj_begin);
+        }
+        return static_cast<int32_t>(i);
+    }
+    Child4 child(uint32_t i) const {
+        const rt_bvh_node &nd = src.nodes[i];
+        return Child4{link_of(i), {nd.bmin[0], nd.bmin[1], nd.bmin[2]}, {nd.bmax[0], nd.bmax[1], nd.bmax[2]}};
+    }
+    // the 2..4 children of the wide node rooted at binary inner node `bin` (largest box opened first, as collapse4)
+    Node4Boxes open(int32_t bin) const {
+        Node4Boxes nb;
+        nb.n = 2;
+        nb.ch[0] = child(src.nodes[bin].left_child);
+        nb.ch[1] = child(src.nodes[bin].right_child);
+        while (nb.n < 4) {
+            int best = -1;
+            float best_area = -1.0f;
+            for (int i = 0; i < nb.n; ++i)
+                if (nb.ch[i].link >= 0 && box_area(nb.ch[i]) > best_area) {
+                    best_area = box_area(nb.ch[i]);
+                    best = i;
+                }
+            if (best < 0) break;
+            const rt_bvh_node &nd = src.nodes[nb.ch[best].link];
+            nb.ch[best] = child(nd.left_child);
+            nb.ch[nb.n++] = child(nd.right_child);
+        }
+        return nb;
+    }
+    // serial collapse of a sub-tree into (out, boxes); returns its root's index in `out`
+    int32_t collapse(int32_t bin, std::vector<QNode4> &out, std::vector<Node4Boxes> &boxes) const {
+        const Node4Boxes nb = open(bin);
+        const int32_t idx = static_cast<int32_t>(out.size());
+        out.emplace_back();
+        boxes.push_back(nb);
+        int32_t links[4];
+        for (int i = 0; i < 4; ++i)
+            links[i] = i < nb.n ? (nb.ch[i].link >= 0 ? collapse(nb.ch[i].link, out, boxes) : nb.ch[i].link) : null_leaf;
+        QNode4 &q = out[idx];
+        std::memset(&q, 0, sizeof q);
+        for (int i = 0; i < 4; ++i) q.link[i] = links[i];
+        return idx;
+    }
+};
+inline int32_t collapse4_built(const rt_bvh_desc &src, std::vector<DTri> &tris, int32_t null_leaf, std::vector<QNode4> &out,
+                               std::vector<Node4Boxes> &boxes) {
+    const Built4 b{src, tris, null_leaf};
+    const int32_t root_link = b.link_of(src.root);
+    if (root_link < 0) return root_link;  // the whole tree is one leaf
+    struct Task {
+        int32_t bin;
+        uint32_t parent;
+        int slot;
+        std::vector<QNode4> nodes;
+        std::vector<Node4Boxes> boxes;
+    };
+    std::vector<Task> tasks;
+    // top levels, breadth first: (binary node, wide parent, slot, depth)
+    struct Top {
+        int32_t bin;
+        uint32_t parent;
+        int slot, depth;
+    };
+    std::vector<Top> queue{{root_link, 0u, -1, 0}};
+    for (size_t qi = 0; qi < queue.size(); ++qi) {
+        const Top t = queue[qi];
+        const Node4Boxes nb = b.open(t.bin);
+        const uint32_t idx = static_cast<uint32_t>(out.size());
+        out.emplace_back();
+        boxes.push_back(nb);
+        std::memset(&out[idx], 0, sizeof(QNode4));
+        if (t.slot >= 0) out[t.parent].link[t.slot] = static_cast<int32_t>(idx);
+        for (int i = 0; i < 4; ++i) {
+            if (i >= nb.n) {
+                out[idx].link[i] = null_leaf;
+            } else if (nb.ch[i].link < 0) {
+                out[idx].link[i] = nb.ch[i].link;
+            } else if (t.depth < 2) {
+                queue.push_back({nb.ch[i].link, idx, i, t.depth + 1});
+            } else {
+                tasks.emplace_back();
+                tasks.back().bin = nb.ch[i].link;
+                tasks.back().parent = idx;
+                tasks.back().slot = i;
+            }
+        }
+    }
+    // sub-trees in parallel (dynamic hand-out: their sizes differ)
+    std::atomic<size_t> next{0};
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::min<unsigned>(hw ? hw : 1, 16), tasks.size());
+    auto worker = [&] {
+        for (size_t k = next++; k < tasks.size(); k = next++) b.collapse(tasks[k].bin, tasks[k].nodes, tasks[k].boxes);
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(worker);
+    worker();
+    for (auto &x : th) x.join();
+    // append: task k's nodes start at base[k]
+    std::vector<size_t> base(tasks.size() + 1, out.size());
+    for (size_t k = 0; k < tasks.size(); ++k) base[k + 1] = base[k] + tasks[k].nodes.size();
+    out.resize(base.back());
+    boxes.resize(base.back());
+    next = 0;
+    auto copier = [&] {
+        for (size_t k = next++; k < tasks.size(); k = next++) {
+            const int32_t off = static_cast<int32_t>(base[k]);
+            for (size_t i = 0; i < tasks[k].nodes.size(); ++i) {
+                QNode4 q = tasks[k].nodes[i];
+                for (int c = 0; c < 4; ++c)
+                    if (q.link[c] >= 0) q.link[c] += off;
+                out[base[k] + i] = q;
+                boxes[base[k] + i] = tasks[k].boxes[i];
+            }
+            out[tasks[k].parent].link[tasks[k].slot] = off;  // the sub-tree's root is its first node
+        }
+    };
+    th.clear();
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(copier);
+    copier();
+    for (auto &x : th) x.join();
+    return 0;
+}
+
 // ---- 8-wide collapse (QNode8) ---------------------------------------------------------------------------------
 constexpr uint32_t kLeaf8 = 3;  // triangles per leaf child (2 count bits per slot)
 #ifndef RT_COLLAPSE8_OPTIMAL
@@ -590,7 +728,8 @@ inline int quantize_nodes8(const std::vector<Node8Boxes> &boxes, std::vector<QNo
 // `formats`: which quantised node arrays to produce (the device build needs one, the host checks both)
 // RT_PACK_Q8 re-orders the triangles, so it excludes the other two
 enum { RT_PACK_Q2 = 1, RT_PACK_Q4 = 2, RT_PACK_ALL = 3, RT_PACK_Q8 = 4 };
-inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &out, int formats = RT_PACK_ALL) {
+// `built_tree`: src comes from sah_build.h (well formed), which allows the direct parallel 4-wide collapse
+inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &out, int formats = RT_PACK_ALL, bool built_tree = false) {
     out.nodes.clear();
     out.tris.assign(src.n_objects, DTri());
     out.order.assign(src.objects, src.objects + src.n_objects);
@@ -615,6 +754,22 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
         }
     });
     if (src.root == RT_NO_CHILD || src.n_objects == 0) return RT_OK;
+    if (built_tree && formats == RT_PACK_Q4) {
+        DTri null_tri;
+        std::memset(&null_tri, 0, sizeof null_tri);
+        null_tri.id_last = RT_LAST_BIT;
+        out.tris.push_back(null_tri);
+        const int32_t null_leaf = ~static_cast<int32_t>(out.tris.size() - 1);
+        std::vector<detail::Node4Boxes> boxes;
+        out.qnodes4.reserve(src.n_nodes / 3 + 64);
+        boxes.reserve(src.n_nodes / 3 + 64);
+        lap.lap(1);
+        out.root4 = detail::collapse4_built(src, out.tris, null_leaf, out.qnodes4, boxes);
+        lap.lap(2);
+        if (int rq = detail::quantize_nodes4(boxes, out.qnodes4)) return rq;
+        lap.lap(3);
+        return RT_OK;
+    }
     int rc = RT_OK;
     out.root = detail::pack_node(src, src.root, out, 0, rc);
     if (rc) return rc;
@@ -683,7 +838,7 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
     if (rebuild_scene_bvh && sc.scene_bvh.n_objects > 0 && sc.scene_bvh.root != RT_NO_CHILD) {
         build_sah_bvh(sc.tri_pos, sc.scene_bvh.objects, sc.scene_bvh.n_objects, out.built, &out.sah_scratch);
         lap.lap(0);
-        if (int rc = pack_bvh(sc, out.built.desc(), out.scene, formats)) return rc;
+        if (int rc = pack_bvh(sc, out.built.desc(), out.scene, formats, true)) return rc;
     } else if (int rc = pack_bvh(sc, sc.scene_bvh, out.scene, formats)) {
         return rc;
     }
@@ -697,7 +852,7 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
         } else if (rebuild_scene_bvh && sc.light_bvh.n_objects > 0 && sc.light_bvh.root != RT_NO_CHILD) {
             BuiltBvh built;
             build_sah_bvh(sc.tri_pos, sc.light_bvh.objects, sc.light_bvh.n_objects, built);
-            if (int rc = pack_bvh(sc, built.desc(), out.light, formats)) return rc;
+            if (int rc = pack_bvh(sc, built.desc(), out.light, formats, true)) return rc;
         } else {
             out.light = host_order;
         }

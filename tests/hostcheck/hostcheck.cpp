@@ -70,6 +70,29 @@ extern "C" {
 void hc_set_rebuild(int on) { g_rebuild = on != 0; }
 void hc_set_wide8(int on) { g_wide8 = on != 0; }
 
+// Primary ids through the upload path's own packing: library-built tree + direct parallel 4-wide collapse
+// (pack_bvh's built_tree fast path, formats = RT_PACK_Q4 only); out[0] = wide nodes, out[1] = node steps per ray
+int hc_primary_ids_upload_path(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids, double *out) {
+    HostScene hs;
+    if (int rc = pack_scene(*sc, hs.p, true, RT_PACK_Q4)) return rc;
+    fill_scene_constants(*sc, hs.p, hs.d);
+    hs.d.scene.qnodes4 = hs.p.scene.qnodes4.data();
+    hs.d.scene.tris = hs.p.scene.tris.data();
+    const Camera cam = make_camera(hs.d, w, h);
+    uint64_t steps = 0;
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x) {
+            const f3 dir = camera_dir(cam, (float)x + 0.5f, (float)y + 0.5f);
+            uint32_t st = 0;
+            const Hit hit = closest_hit_q4(hs.d.scene, cam.pos, dir, hs.d.eps, &st);
+            steps += st;
+            ids[(size_t)y * w + x] = hit.tri < 0 ? -1 : (int32_t)(hs.p.scene.tris[hit.tri].id_last & ~RT_LAST_BIT);
+        }
+    out[0] = (double)hs.p.scene.qnodes4.size();
+    out[1] = (double)steps / ((double)w * h);
+    return 0;
+}
+
 // Structure of the 8-wide collapse and node steps of its traversal over the pixel-centre rays:
 // out[0] nodes, out[1] mean children per node, out[2] node steps per ray, out[3] triangles (must equal the scene's)
 int hc_wide8_stats(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids, double *out) {
@@ -212,7 +235,8 @@ int hc_primary_ids_q4(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *
 }
 
 // Wall time of the re-pack phases (ms): out[0] SAH build, out[1] pack_bvh of the scene tree (triangles, nodes, both
-// quantisations, collapse), out[2] whole pack_scene with rebuild.
+// quantisations, collapse), out[2] whole pack_scene with rebuild, out[3] the upload path's pack_scene (4-wide only),
+// out[4..7] its phases.
 int hc_pack_timing(const rt_scene_desc *sc, double *out) {
     using clk = std::chrono::steady_clock;
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -226,7 +250,15 @@ int hc_pack_timing(const rt_scene_desc *sc, double *out) {
     PackedScene ps;
     if (int rc = pack_scene(*sc, ps, true)) return rc;
     auto t3 = clk::now();
-    out[0] = ms(t0, t1); out[1] = ms(t1, t2); out[2] = ms(t2, t3);
+    PackedScene pq;
+    double phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    pack_times() = phase;
+    const int rq = pack_scene(*sc, pq, true, RT_PACK_Q4);  // what rt_gpu_upload_scene runs
+    pack_times() = nullptr;
+    if (rq) return rq;
+    auto t4 = clk::now();
+    out[0] = ms(t0, t1); out[1] = ms(t1, t2); out[2] = ms(t2, t3); out[3] = ms(t3, t4);
+    for (int k = 0; k < 4; ++k) out[4 + k] = phase[k];  // SAH build, triangles (+ binary nodes), collapse, quantise
     return 0;
 }
 

@@ -293,6 +293,37 @@ def test_eight_wide_traversal_gives_reference_ids(name, rebuild, hc, manifest, g
     assert int(out[3]) == d.n_tris
 
 
+@pytest.mark.parametrize("name", SMALL)
+def test_upload_path_packing_gives_reference_ids(name, hc, manifest, golden_scene):
+    """rt_gpu_upload_scene's packing (library-built tree, direct parallel 4-wide collapse without the binary node array)
+    finds the reference's hits."""
+    m = manifest["scenes"][name]
+    w, h = m["width"], m["height"]
+    d = golden_scene(name).desc()
+    ids = np.zeros((h, w), np.int32)
+    out = (C.c_double * 2)()
+    assert hc.hc_primary_ids_upload_path(C.byref(d), w, h, ids.ctypes.data_as(C.c_void_p), out) == 0
+    ref = golden_array(f"{name}_ids.i32", np.int32, (h, w))
+    assert (ids == ref).mean() >= 0.999
+
+
+def test_upload_path_packing_on_the_260k_scene(hc, big_scene):
+    """Same wide tree as the serial collapse over the binary node array: same number of nodes, same node steps, same ids."""
+    d = big_scene.desc()
+    ids_a = np.zeros((96, 96), np.int32)
+    ids_b = np.zeros((96, 96), np.int32)
+    out = (C.c_double * 2)()
+    steps = (C.c_uint64 * 2)()
+    assert hc.hc_primary_ids_upload_path(C.byref(d), 96, 96, ids_a.ctypes.data_as(C.c_void_p), out) == 0
+    hc.hc_set_rebuild(1)
+    try:
+        assert hc.hc_primary_ids_q4(C.byref(d), 96, 96, ids_b.ctypes.data_as(C.c_void_p), steps) == 0
+    finally:
+        hc.hc_set_rebuild(0)
+    assert (ids_a == ids_b).all()
+    assert abs(out[1] * 96 * 96 - steps[0]) < 0.5
+
+
 def test_eight_wide_collapse_on_the_260k_scene(hc, big_scene):
     d = big_scene.desc()
     ids8 = np.zeros((96, 96), np.int32)
