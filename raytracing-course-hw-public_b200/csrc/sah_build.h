@@ -105,6 +105,7 @@ struct Prim {  // 40 bytes, one per triangle
 
 struct Ctx {
     std::vector<Prim> prims;  // permuted in place
+    std::vector<Prim> tmp;    // scatter target of the parallel partition near the root
     std::vector<rt_bvh_node> nodes;
 };
 
@@ -231,6 +232,75 @@ inline void build_range(Ctx &cx, uint32_t slot, uint32_t b, uint32_t e, const Bo
             const float pmin = cmin[axis], pscale = scale[axis];
             lbox.reset(); rbox.reset(); lcb.reset(); rcb.reset();
             uint32_t i = b, j = e;
+            uint32_t ntp = 1;
+            if (n >= 4 * kParallelMin && depth < kParallelDepth) {  // (hardware_concurrency() is a system call: only here)
+                const unsigned hw_p = std::thread::hardware_concurrency();
+                ntp = std::max(1u, std::min(hw_p ? hw_p : 1u, std::min(16u >> depth, n / kParallelMin)));
+            }
+            if (ntp > 1) {
+                // large ranges near the root: count + bound per chunk, scatter into cx.tmp at the chunks' offsets, copy back
+                // (the serial in-place partition of the top four levels was the builder's longest serial stretch)
+                struct Part {
+                    uint32_t left = 0;
+                    Box3 lb, rb, lc, rc;
+                };
+                std::vector<Part> part(ntp);
+                const uint32_t chunk = (n + ntp - 1) / ntp;
+                auto bin_of = [=](const Prim &pr) {
+                    int k = static_cast<int>((pr.c[axis] - pmin) * pscale);
+                    return k < 0 ? 0 : (k >= nb ? nb - 1 : k);
+                };
+                auto run = [&](auto fn) {
+                    std::vector<std::thread> th;
+                    for (uint32_t t = 1; t < ntp; ++t) th.emplace_back([&fn, t] { fn(t); });
+                    fn(0u);
+                    for (auto &x : th) x.join();
+                };
+                run([&](uint32_t t) {
+                    Part pt;  // thread-local; stored once at the end (neighbouring Parts share cache lines)
+                    pt.lb.reset(); pt.rb.reset(); pt.lc.reset(); pt.rc.reset();
+                    const uint32_t cb = b + std::min(n, t * chunk), ce = b + std::min(n, (t + 1) * chunk);
+                    for (uint32_t q = cb; q < ce; ++q) {
+                        if (bin_of(P[q]) <= best_bin) {
+                            ++pt.left;
+                            pt.lb.grow(P[q].lo, P[q].hi);
+                            pt.lc.grow(P[q].c, P[q].c);
+                        } else {
+                            pt.rb.grow(P[q].lo, P[q].hi);
+                            pt.rc.grow(P[q].c, P[q].c);
+                        }
+                    }
+                    part[t] = pt;
+                });
+                uint32_t total_left = 0;
+                for (uint32_t t = 0; t < ntp; ++t) total_left += part[t].left;
+                std::vector<uint32_t> loff(ntp), roff(ntp);
+                uint32_t lo_acc = b, ro_acc = b + total_left;
+                for (uint32_t t = 0; t < ntp; ++t) {
+                    const uint32_t cb = b + std::min(n, t * chunk), ce = b + std::min(n, (t + 1) * chunk);
+                    loff[t] = lo_acc;
+                    roff[t] = ro_acc;
+                    lo_acc += part[t].left;
+                    ro_acc += (ce - cb) - part[t].left;
+                    if (part[t].left) { lbox.grow(part[t].lb); lcb.grow(part[t].lc); }
+                    if (part[t].left < ce - cb) { rbox.grow(part[t].rb); rcb.grow(part[t].rc); }
+                }
+                Prim *T = cx.tmp.data();
+                run([&](uint32_t t) {
+                    const uint32_t cb = b + std::min(n, t * chunk), ce = b + std::min(n, (t + 1) * chunk);
+                    uint32_t l = loff[t], r = roff[t];
+                    for (uint32_t q = cb; q < ce; ++q) {
+                        if (bin_of(P[q]) <= best_bin) T[l++] = P[q];
+                        else T[r++] = P[q];
+                    }
+                });
+                run([&](uint32_t t) {
+                    const uint32_t cb = b + std::min(n, t * chunk), ce = b + std::min(n, (t + 1) * chunk);
+                    std::memcpy(P + cb, T + cb, static_cast<size_t>(ce - cb) * sizeof(Prim));
+                });
+                i = b + total_left;
+                j = i;
+            }
             while (i < j) {  // in-place partition by bin index
                 int k = static_cast<int>((P[i].c[axis] - pmin) * pscale);
                 k = k < 0 ? 0 : (k >= nb ? nb - 1 : k);
@@ -306,6 +376,7 @@ inline void build_sah_bvh(const float *tri_pos, const uint32_t *ids, uint32_t n,
     sah::Ctx local;
     sah::Ctx &cx = scratch ? *scratch : local;
     cx.prims.resize(n);
+    cx.tmp.resize(n);
     sah::Box3 box, cbox;
     box.reset();
     cbox.reset();
