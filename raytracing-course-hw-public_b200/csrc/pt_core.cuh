@@ -2,7 +2,7 @@
 //
 // Everything here is a pure function of its arguments and is marked RT_HD so that the same source
 // can also be compiled by the host compiler for unit tests of the math (tests/hostcheck); the
-// kernels in kernels.cu only add the queue plumbing.  Each function cites the reference code whose
+// kernels in kernels.cuh / extend8.cuh only add the queue plumbing.  Each function cites the reference code whose
 // semantics it has to keep (Appendix B of SURVEY.md lists why each detail matters).
 #ifndef RT_PT_CORE_CUH
 #define RT_PT_CORE_CUH
@@ -188,7 +188,8 @@ RT_HD bool tri_test(f3 a, f3 e1, f3 e2, f3 o, f3 d, float min_dst, float &t, flo
     return beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= min_dst;
 }
 
-// ---- quantised node (QNode, rt_types.h): both child slab tests from one 32-byte record --------------------
+// ---- quantised 2-wide node (QNode, rt_types.h): both child slab tests from one 32-byte record.  Host checks only
+// (the device traversed this form before the 4-wide one); qplane() below is shared by all node widths. --------------
 // Plane byte q of a word -> the float 1 + q * 2^-16 (q added into mantissa bits 7..14), so that
 //   t(q) = (org + q * cell - o) / d = fma(1 + q * 2^-16, A, B)   with  A = 2^16 * cell / d,  B = (org - o) / d - A
 // costs one byte-dot-product + one FFMA per plane and no integer->float conversion.  The extraction is a DP4A
