@@ -3,7 +3,9 @@
 // functions the CUDA kernels call (traversal, hit shading data, samplers, pdfs, BRDF, Philox lanes)
 // with the oracle without a GPU.  It is NOT a render path of the product: librt_gpu.so does not
 // contain or call any of this, and nothing outside tests/ builds or loads it.
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -90,6 +92,98 @@ int hc_primary_ids_upload_path(const rt_scene_desc *sc, uint32_t w, uint32_t h, 
         }
     out[0] = (double)hs.p.scene.qnodes4.size();
     out[1] = (double)steps / ((double)w * h);
+    return 0;
+}
+
+// ---- containment invariant of the wide node formats ------------------------------------------------------------------
+// Every decoded child box must contain every vertex (as the device forms it: a, a + e1, a + e2, evaluated exactly) of
+// every triangle below that child — whatever builder, collapse and quantisation produced the tree.
+namespace {
+struct BoxD {
+    double lo[3], hi[3];
+    void reset() {
+        for (int k = 0; k < 3; ++k) lo[k] = 1e300, hi[k] = -1e300;
+    }
+    void grow(const BoxD &b) {
+        for (int k = 0; k < 3; ++k) lo[k] = std::min(lo[k], b.lo[k]), hi[k] = std::max(hi[k], b.hi[k]);
+    }
+};
+BoxD tri_run_box(const std::vector<DTri> &tris, uint32_t first, uint32_t count_or_0, uint64_t &n_tris) {
+    BoxD b;
+    b.reset();
+    for (uint32_t k = first;; ++k) {
+        const DTri &t = tris[k];
+        const double v[3][3] = {{t.ax, t.ay, t.az},
+                                {(double)t.ax + t.e1x, (double)t.ay + t.e1y, (double)t.az + t.e1z},
+                                {(double)t.ax + t.e2x, (double)t.ay + t.e2y, (double)t.az + t.e2z}};
+        for (auto &p : v)
+            for (int a = 0; a < 3; ++a) b.lo[a] = std::min(b.lo[a], p[a]), b.hi[a] = std::max(b.hi[a], p[a]);
+        ++n_tris;
+        if (count_or_0 ? k + 1 == first + count_or_0 : (t.id_last & RT_LAST_BIT) != 0) break;
+    }
+    return b;
+}
+double plane_of(uint32_t org_word, uint32_t byte) { return (double)u2f(org_word) + byte * ldexp(1.0, (int)(org_word & 255u) - 127); }
+void check_child(const BoxD &exact, const uint32_t org[3], const uint32_t qlo[3], const uint32_t qhi[3], uint64_t &bad, uint64_t &checked) {
+    for (int a = 0; a < 3; ++a) {
+        ++checked;
+        if (plane_of(org[a], qlo[a]) > exact.lo[a] || plane_of(org[a], qhi[a]) < exact.hi[a]) ++bad;
+    }
+}
+BoxD walk4(const PackedBvh &b, int32_t link, uint64_t &bad, uint64_t &checked, uint64_t &n_tris, int32_t null_leaf) {
+    if (link < 0) return tri_run_box(b.tris, (uint32_t)~link, 0, n_tris);
+    const QNode4 &q = b.qnodes4[link];
+    BoxD all;
+    all.reset();
+    for (int c = 0; c < 4; ++c) {
+        if (q.link[c] == null_leaf) continue;
+        const BoxD e = walk4(b, q.link[c], bad, checked, n_tris, null_leaf);
+        const uint32_t lo[3] = {(q.lo[0] >> 8 * c) & 255u, (q.lo[1] >> 8 * c) & 255u, (q.lo[2] >> 8 * c) & 255u};
+        const uint32_t hi[3] = {(q.hi[0] >> 8 * c) & 255u, (q.hi[1] >> 8 * c) & 255u, (q.hi[2] >> 8 * c) & 255u};
+        check_child(e, q.org, lo, hi, bad, checked);
+        all.grow(e);
+    }
+    return all;
+}
+BoxD walk8(const PackedBvh &b, uint32_t node, uint64_t &bad, uint64_t &checked, uint64_t &n_tris) {
+    const QNode8 &q = b.qnodes8[node];
+    BoxD all;
+    all.reset();
+    uint32_t rank = 0;
+    for (uint32_t s = 0; s < 8; ++s) {
+        const uint32_t cnt = (q.counts >> (2 * s)) & 3u;
+        const bool inner = (q.imask >> s) & 1u;
+        if (!inner && !cnt) continue;
+        const BoxD e = inner ? walk8(b, q.child_base + rank++, bad, checked, n_tris)
+                             : tri_run_box(b.tris, q.tri_base + leaf8_offset(q.counts, s), cnt, n_tris);
+        const uint32_t *g = s < 4 ? q.g0 : q.g1;
+        const int c = (int)(s & 3u);
+        const uint32_t lo[3] = {(g[0] >> 8 * c) & 255u, (g[1] >> 8 * c) & 255u, (g[2] >> 8 * c) & 255u};
+        const uint32_t hi[3] = {(g[3] >> 8 * c) & 255u, (g[4] >> 8 * c) & 255u, (g[5] >> 8 * c) & 255u};
+        check_child(e, q.org, lo, hi, bad, checked);
+        all.grow(e);
+    }
+    return all;
+}
+}  // namespace
+
+// width 4 or 8; `upload_path`: pack like rt_gpu_upload_scene (library-built tree, wide format only).
+// out[0] child planes checked (pairs), out[1] violations, out[2] triangles reached (must equal the scene's)
+int hc_wide_containment(const rt_scene_desc *sc, int width, int upload_path, double *out) {
+    PackedScene p;
+    const int formats = width == 8 ? RT_PACK_Q8 : (upload_path ? RT_PACK_Q4 : RT_PACK_ALL);
+    if (int rc = pack_scene(*sc, p, upload_path != 0 || g_rebuild, formats)) return rc;
+    uint64_t bad = 0, checked = 0, n_tris = 0;
+    for (const PackedBvh *b : {&p.scene, &p.light}) {
+        if (width == 8) {
+            if (!b->qnodes8.empty()) walk8(*b, 0, bad, checked, n_tris);
+        } else if (b->root4 != RT_LINK_NONE) {
+            walk4(*b, b->root4, bad, checked, n_tris, ~static_cast<int32_t>(b->tris.size() - 1));
+        }
+    }
+    out[0] = (double)checked;
+    out[1] = (double)bad;
+    out[2] = (double)n_tris;
     return 0;
 }
 

@@ -293,6 +293,24 @@ def test_eight_wide_traversal_gives_reference_ids(name, rebuild, hc, manifest, g
     assert int(out[3]) == d.n_tris
 
 
+@pytest.mark.parametrize("width,upload_path,rebuild", [(4, 0, 0), (4, 0, 1), (4, 1, 1), (8, 0, 0), (8, 0, 1)])
+@pytest.mark.parametrize("name", SMALL + ["big"])
+def test_wide_nodes_contain_their_triangles(name, width, upload_path, rebuild, hc, golden_scene, big_scene):
+    """Containment invariant of QNode4 / QNode8, whatever built, collapsed and quantised the tree: every decoded child
+    box holds every vertex of every triangle below it, and the tree reaches every triangle (scene + light BVH) once."""
+    sc = big_scene if name == "big" else golden_scene(name)
+    d = sc.desc()
+    out = (C.c_double * 3)()
+    hc.hc_set_rebuild(rebuild)
+    try:
+        assert hc.hc_wide_containment(C.byref(d), width, upload_path, out) == 0
+    finally:
+        hc.hc_set_rebuild(0)
+    assert out[0] > 0
+    assert out[1] == 0
+    assert int(out[2]) == d.n_tris + d.light_bvh.n_objects
+
+
 @pytest.mark.parametrize("name", SMALL)
 def test_upload_path_packing_gives_reference_ids(name, hc, manifest, golden_scene):
     """rt_gpu_upload_scene's packing (library-built tree, direct parallel 4-wide collapse without the binary node array)
