@@ -2,10 +2,14 @@
 """bench.py — Msamples/s of the path-tracing hot path on B200 (BASELINE.json metric).
 
 Workload (config 4 of BASELINE.json): the synthetic "Sponza-scale" glTF of SURVEY.md 8(d) — 260 192 triangles,
-textured, 32 emissive triangles — at 1000 x 1000 pixels, 1000 spp per GPU.  One step = one full render
-(1e9 pixel-samples per GPU).  With N GPUs (one process per GPU, torchrun) rank r renders samples
-[1000 r, 1000 (r+1)) of every pixel, i.e. a 1000 N spp image ("weak" scaling), followed by the path's single
+textured, 32 emissive triangles — at 1000 x 1000 pixels, 1000 spp.  One step = one full render of that image
+(1e9 pixel-samples).  With N GPUs (one process per GPU, torchrun) the FIXED 1000 spp are split: rank r renders
+samples [1000 r / N, 1000 (r+1) / N) of every pixel ("strong" scaling — the north star's "1000x1000, 1000 spp on
+8 x B200", the GPU analogue of the reference's span pool, raytracer.h:635-665), followed by the path's single
 collective: one NCCL reduce(sum) of the W*H*4 float accumulation buffer to rank 0, inside the timed region.
+`--scaling weak` renders 1000 spp PER GPU instead (a 1000 N spp image); `--config c5` is BASELINE config 5
+(3840 x 2160, 4096 spp split over the ranks).  After the timed region an N > 1 run CHECKS its reduced image against
+a single-GPU render of the same sample set on rank 0 (`parity_check`).
 
   value        device-timed (CUDA events) samples/s of K steps, scene resident in HBM
   e2e          the same through the public C ABI with host buffers every step: rt_gpu_upload_scene (host
@@ -31,7 +35,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "scenes")]
 
 SCENE = "big_lights"
 WIDTH = HEIGHT = 1000
-SPP_PER_GPU = 1000
+SPP = 1000
 METRIC = "Msamples/s"
 FLOP_BOX, FLOP_TRI = 24.0, 70.0  # slab test, Cramer triangle test
 
@@ -180,6 +184,8 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
+    world = args.gpus
+    spp_total = args.spp * world if args.scaling == "weak" else args.spp
     # each step is a bounded sample sized so that the whole run ends within a few minutes
     per_step = max(2.0, min(20.0, 150.0 / max(steps + warm, 1)))
     vals = []
@@ -188,34 +194,34 @@ def run_reference_arm(args, rank):
         if i >= warm:
             vals.append(r)
     v = sum(x["value"] for x in vals) / len(vals)
-    samples_per_step = WIDTH * HEIGHT * SPP_PER_GPU
+    samples_per_step = args.width * args.height * spp_total
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
            "warmup": warm, "ms_per_step": samples_per_step / (v * 1e6) * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": v / 0.355, "dtype": "f32", "data": "synthetic",
-           "config": config_dict(args.gpus, extra={"note": "CPU arm: each step is a bounded sample (250x250) of the "
-                                                           "workload; ms_per_step is the extrapolated full step"}),
+           "scaling": args.scaling, "vs_baseline": v / 0.355, "dtype": "f32", "data": "synthetic",
+           "config": config_dict(args, world),
+           "note": "CPU arm: each step is a bounded sample (250x250) of the workload; ms_per_step is the "
+                   "extrapolated full step",
            "cpu_baseline": {**vals[-1], "value": v},
            "e2e": {"value": v, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
 
 
-def config_dict(n_gpus, extra=None):
-    e = extra or {}
-    w, h, spp = e.get("width", WIDTH), e.get("height", HEIGHT), e.get("spp_per_gpu", SPP_PER_GPU)
-    name = "BASELINE config 4"
-    if (w, h) == (3840, 2160) and spp * n_gpus == 4096:
+def config_dict(args, n_gpus):
+    """The workload both arms are quoted on (identical keys and values for --impl b200 and --impl reference)."""
+    w, h = args.width, args.height
+    spp_total = args.spp * n_gpus if args.scaling == "weak" else args.spp
+    if (w, h, spp_total) == (WIDTH, HEIGHT, SPP):
+        name = "BASELINE config 4"
+    elif (w, h, spp_total) == (3840, 2160, 4096):
         name = "BASELINE config 5"
-    elif (w, h, spp) != (WIDTH, HEIGHT, SPP_PER_GPU):
+    else:
         name = "BASELINE config 4 scene at a non-default size"
-    c = {"workload": f"{name}: synthetic Sponza-scale glTF '{e.get('scene', SCENE)}' (260192 triangles, textured, 32 "
-                     f"emissive), {w}x{h}, {spp} spp per GPU, ray depth 8",
-         "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP_PER_GPU, "spp_total": SPP_PER_GPU * n_gpus,
-         "parallelism": f"sample-split x{n_gpus} + 1 NCCL reduce" if n_gpus > 1 else "single GPU",
-         "l2": "256 MiB written between steps; per-step path-queue traffic (>100 GB) far exceeds the 126 MB L2"}
-    if extra:
-        c.update(extra)
-    return c
+    return {"workload": f"{name}: synthetic Sponza-scale glTF '{args.scene}' (260192 triangles, textured, 32 emissive), "
+                        f"{w}x{h}, {spp_total} spp, ray depth 8",
+            "scene": args.scene, "width": w, "height": h, "spp_total": spp_total, "spp_per_gpu": spp_total / n_gpus,
+            "parallelism": f"sample-split x{n_gpus} + 1 NCCL reduce" if n_gpus > 1 else "single GPU",
+            "l2": "256 MiB written between steps; per-step path-queue traffic (>100 GB) far exceeds the 126 MB L2"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -242,8 +248,8 @@ def run_gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    w, h, spp_gpu = args.width, args.height, args.spp
-    spp_total = spp_gpu * world
+    w, h = args.width, args.height
+    spp_total = args.spp * world if args.scaling == "weak" else args.spp
     t0 = time.perf_counter()
     scene = gl.load_gltf(scene_path(args.scene), w / h)
     t_load = time.perf_counter() - t0
@@ -287,8 +293,11 @@ def run_gpu_arm(args, rank, world, local_rank):
     samples_all = float(w) * h * spp_total * args.steps
     value = samples_all / (total_ms * 1e-3) / 1e6
 
+    # the N-rank image of the last timed step, for the parity check below
+    img_n = rt.readback()[0] if (rank == 0 and world > 1) else None
+
     # ---- e2e: host buffers every step through the C ABI ------------------------------------------------
-    host_out = np.empty((h, w, 3), np.float32)
+    host_out = torch.empty((h, w, 3), dtype=torch.float32, pin_memory=True).numpy()  # pinned: the D2H lands directly
     scene_bytes = sum(a.nbytes for a in scene._sections() if a is not None)
 
     def e2e_step():
@@ -308,6 +317,34 @@ def run_gpu_arm(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = samples_all / float(e2e_s.item()) / 1e6
+
+    # ---- parity of the multi-GPU result (N > 1): the reduced image == one GPU rendering the same samples ------
+    # (reference semantics: the union of the spans, raytracer.h:639-659; Philox is keyed by the global sample index,
+    # so only the float summation order differs).  Two checks: the benchmark's own image (full spp, unless that
+    # would take more than a few seconds on one GPU), and a 16-spp image at the multi-GPU test's tolerance.
+    parity = None
+    if world > 1:
+        chk_spp = max(16, 2 * world)
+        rtdist.render_distributed(rt, w, h, chk_spp, seed, rank, world, local_rank, args.paths)
+        small_n = rt.readback()[0] if rank == 0 else None
+        barrier()
+        if rank == 0:
+            def cmp(a, b, rtol, atol):
+                fin = np.isfinite(b)
+                rel = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-6)
+                return {"max_rel": float(rel.max()) if rel.size else 0.0, "rtol": rtol, "atol": atol,
+                        "allclose": bool(np.allclose(a, b, rtol=rtol, atol=atol))}
+
+            rt.render(w, h, chk_spp, seed=seed, max_paths_in_flight=args.paths)
+            parity = {"n_ranks": world, "small": {"spp": chk_spp, **cmp(small_n, rt.readback()[0], 2e-6, 1e-7)}}
+            if float(w) * h * spp_total <= 2.5e9:
+                rt.render(w, h, spp_total, seed=seed, max_paths_in_flight=args.paths)
+                # sequential float sums of up to 512 samples per batch: reordering moves a pixel by ~1e-6 relative
+                parity["bench_image"] = {"spp": spp_total, **cmp(img_n, rt.readback()[0], 2e-5, 1e-6)}
+            parity["max_rel"] = max(v["max_rel"] for v in parity.values() if isinstance(v, dict))
+            parity["ok"] = all(v["allclose"] for v in parity.values() if isinstance(v, dict))
+            log("parity_check", parity)
+        barrier()
 
     # ---- roofline of the dominant kernel + CPU baseline (rank 0 only) ---------------------------------
     roof = cpu = counts = None
@@ -347,14 +384,14 @@ def run_gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": value / 0.355, "dtype": "f32", "data": "synthetic",
-               "config": config_dict(world, {"scene": args.scene, "width": w, "height": h, "spp_per_gpu": spp_gpu,
-                                             "spp_total": spp_total}),
+               "scaling": args.scaling, "vs_baseline": value / 0.355, "dtype": "f32", "data": "synthetic",
+               "config": config_dict(args, world),
                "mrays_per_s": {"extension": float(ray_t[0].item()) / (total_ms * 1e-3) / 1e6,
                                "light_pdf": float(ray_t[1].item()) / (total_ms * 1e-3) / 1e6},
                "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(scene_bytes),
                        "d2h_bytes_per_step": int(w * h * 16)},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+               "parity_check": parity,
                "kernel_ms_profiled_step": kernel_ms, "reference_work_per_ray": counts,
                "host_s": {"load_and_bvh_build": t_load, "first_upload": t_upload},
                "vs_baseline_note": "0.355 Msamples/s = README.md:4 (Sponza 1000x1000x1000spp in ~47 min, unknown CPU)"}
@@ -374,10 +411,17 @@ def main():
     ap.add_argument("--scene", default=SCENE)
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
-    ap.add_argument("--spp", type=int, default=SPP_PER_GPU, help="samples per pixel per GPU")
+    ap.add_argument("--spp", type=int, default=None,
+                    help="samples per pixel of the image (strong scaling: split over the GPUs; weak: per GPU)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--config", default="c4", choices=["c4", "c5"], help="BASELINE config 4 (default) or 5")
     ap.add_argument("--paths", type=int, default=0, help="paths in flight per batch (0 = library default)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
+    if args.config == "c5":
+        args.width, args.height = 3840, 2160
+    if args.spp is None:
+        args.spp = 4096 // (args.gpus if args.scaling == "weak" else 1) if args.config == "c5" else SPP
     _capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -153,7 +153,8 @@ typedef struct rt_render_params {
     uint32_t sample_end;     /* 0 => samples */
     uint32_t mode;           /* rt_render_mode */
     uint64_t seed;           /* Philox key */
-    uint32_t max_paths_in_flight; /* 0 => default (128 Mi paths, at most half of the free device memory) */
+    uint32_t max_paths_in_flight; /* 0 => default: 512 Mi paths (132 B of queue state each = 71 GB), at most half of the
+                                     free device memory; callers that share the device (torch, NCCL) pass a bound */
     uint32_t flags;          /* RT_FLAG_* */
     uint32_t pixel_begin;    /* this call renders the row-major pixels [pixel_begin, pixel_end) only (the other */
     uint32_t pixel_end;      /* pixels' sums stay 0 / untouched); 0 => width * height.  Image-tile split. */

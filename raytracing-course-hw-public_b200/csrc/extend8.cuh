@@ -44,10 +44,10 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT8_MINB)
     k_extend8(DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce,
               uint32_t one) {
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t count = q.count[bounce];
-    const float4 *__restrict__ qo = q.o[bounce & 1];
-    const float4 *__restrict__ qd = q.d[bounce & 1];
-    uint32_t *cursor = q.fetch_ext + bounce;
+    const uint32_t count = q.count[bounce * kCounterStride];
+    const float4 *__restrict__ qo = q.o_in;
+    const float4 *__restrict__ qd = q.d_in;
+    uint32_t *cursor = q.fetch_ext + bounce * kCounterStride;
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
 

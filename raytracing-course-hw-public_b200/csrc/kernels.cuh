@@ -39,10 +39,19 @@ struct BatchParams {
     uint32_t centre;    // 1: pixel-centre rays without jitter (gen_ray(camera, x, y), raytracer.h:516-525)
 };
 
+// The ping-pong parity is resolved on the HOST (in = queue b, out = queue b + 1): indexing pointer arrays of a kernel
+// parameter with a run-time `bounce & 1` makes nvcc copy the whole parameter to local memory and re-load the
+// pointers with LDL inside k_shade's loop (round 1: 37 % of its load requests).
 struct Queues {
-    float4 *o[2], *d[2], *thr[2];
+    const float4 *o_in, *d_in, *thr_in;  // queue b   (k_generate writes queue 0 through the *_out pointers)
+    float4 *o_out, *d_out, *thr_out;     // queue b+1
     float4 *hit;
     float4 *rad;
+    // Every counter sits in its own 256-byte line (index * kCounterStride).  Packed into one line (round 1), k_shade ran
+    // 13 % slower whenever a small allocation preceded the queue arena (the "one process in six" / every NCCL rank
+    // slow mode: 28.4 instead of 25.0 ms per 128 spp, reproducible with a 2 MB dummy cudaMalloc); padded, both
+    // placements run at 25.0 (profiles/r2_bimodal.md).  Fewer atomics (128 entries per fetch, output slots reserved in
+    // per-warp chunks) were measured as well and are slower (27.3: the extra loop level costs 8 registers).
     uint32_t *count;        // [ray_depth + 1] queue sizes
     uint32_t *fetch_ext;    // [ray_depth] work-fetch cursors of k_extend
     uint32_t *fetch_shade;  // [ray_depth] work-fetch cursors of k_shade
@@ -73,24 +82,12 @@ template <int BIT> __device__ __forceinline__ void q_store(float *p, float v) {
 
 constexpr int kExtendThreads = 128;
 constexpr int kShadeThreads = 128;
+#ifndef RT_COUNTER_STRIDE
+#define RT_COUNTER_STRIDE 64  // uint32 per counter slot (256 B); 1 = packed (round 1)
+#endif
+constexpr uint32_t kCounterStride = RT_COUNTER_STRIDE;
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-
-// warp pulls the next 32 queue entries; returns the index of this lane's entry (may be >= count)
-__device__ __forceinline__ uint32_t warp_fetch(uint32_t *cursor) {
-    uint32_t base = 0;
-    if (lane_id() == 0) base = atomicAdd(cursor, 32u);
-    return __shfl_sync(0xFFFFFFFFu, base, 0) + lane_id();
-}
-
-// warp-aggregated append: one atomicAdd per warp, slots handed out by __popc of the lower lanes
-__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool active) {
-    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, active);
-    uint32_t base = 0;
-    if (lane_id() == 0 && mask) base = atomicAdd(counter, static_cast<uint32_t>(__popc(mask)));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    return base + static_cast<uint32_t>(__popc(mask & ((1u << lane_id()) - 1u)));
-}
 
 __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Queues q) {
     const uint32_t n = bp.npix * bp.k;
@@ -113,9 +110,9 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
         jy = u01(r.y);
     }
     const f3 dir = camera_dir(cam, static_cast<float>(px) + jx, static_cast<float>(py) + jy);
-    q_store<2>(q.o[0] + slot, make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel)));
-    q_store<2>(q.d[0] + slot, make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample)));
-    q_store<2>(q.thr[0] + slot, make_float4(1.0f, 1.0f, 1.0f, -1.0f));
+    q_store<2>(q.o_out + slot, make_float4(cam.pos.x, cam.pos.y, cam.pos.z, __uint_as_float(pixel)));
+    q_store<2>(q.d_out + slot, make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample)));
+    q_store<2>(q.thr_out + slot, make_float4(1.0f, 1.0f, 1.0f, -1.0f));
     q_store<3>(q.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
@@ -183,10 +180,10 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
              uint32_t one) {
     // `one` = 0x3F800000, passed as an argument so that it is not an immediate (see qplane() in pt_core.cuh)
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t count = q.count[bounce];
-    const float4 *__restrict__ qo = q.o[bounce & 1];
-    const float4 *__restrict__ qd = q.d[bounce & 1];
-    uint32_t *cursor = q.fetch_ext + bounce;
+    const uint32_t count = q.count[bounce * kCounterStride];
+    const float4 *__restrict__ qo = q.o_in;
+    const float4 *__restrict__ qd = q.d_in;
+    uint32_t *cursor = q.fetch_ext + bounce * kCounterStride;
     const uint32_t lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -200,7 +197,9 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
         l = static_cast<int32_t>(e_.x);  \
         t = __uint_as_float(e_.y);       \
     } while (0)
-    float2 overflow[96 - kSmemStack];  // up to three pushes per level of a tree half as deep as the binary one
+    // the deeper part of the stack; the upload path guarantees that no ray needs more than RT_EXT_STACK_CAP entries
+    // (PackedBvh::stack_need4, checked in pack_bvh), so push() carries no bounds check
+    float2 overflow[RT_EXT_STACK_CAP - kSmemStack];
     uint2 *top = s_stack + threadIdx.x;  // slot of the NEXT push (valid while sp < kSmemStack)
     int sp = 0;
     int32_t link = kLinkDone;  // >= 0 inner node, kLinkPop / kLinkDone, otherwise a leaf (~first triangle)
@@ -426,19 +425,25 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
-    const uint32_t count = q.count[bounce];
-    const int in = bounce & 1, out = in ^ 1;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t count = q.count[bounce * kCounterStride];
+    uint32_t *const fetch_cursor = q.fetch_shade + bounce * kCounterStride;
+    uint32_t *const out_counter = q.count + (bounce + 1) * kCounterStride;
     const bool last = bounce + 1 == s.ray_depth;
+    const uint32_t lane = lane_id();
     uint32_t n_light = 0, n_shade = 0, n_ext = 0;
     for (;;) {
-        const uint32_t i = warp_fetch(q.fetch_shade + bounce);
-        if (i - lane_id() >= count) break;
+        uint32_t base = 0;  // the warp pulls the next 32 queue entries
+        if (lane == 0) base = atomicAdd(fetch_cursor, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= count) break;
+        const uint32_t i = base + lane;
         bool alive = false;
         f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), thr = mk3(0, 0, 0), rad = mk3(0, 0, 0);
         float pending = -1.0f;
         uint32_t pixel = 0, sample = 0;
         if (i < count) {
-            const float4 o4 = q_load<1>(q.o[in] + i), d4 = q_load<1>(q.d[in] + i), t4 = q_load<1>(q.thr[in] + i), h4 = q_load<1>(q.hit + i);
+            const float4 o4 = q_load<1>(q.o_in + i), d4 = q_load<1>(q.d_in + i), t4 = q_load<1>(q.thr_in + i), h4 = q_load<1>(q.hit + i);
             o = mk3(o4.x, o4.y, o4.z);
             d = mk3(d4.x, d4.y, d4.z);
             thr = mk3(t4.x, t4.y, t4.z);
@@ -484,11 +489,15 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
                 }
             }
         }
-        const uint32_t dst = warp_append(q.count + bounce + 1, alive);
+        // warp-aggregated append: one atomicAdd per warp, slots handed out by __popc of the lower lanes
+        const uint32_t mask = __ballot_sync(FULL, alive);
+        uint32_t dst = 0;
+        if (lane == 0 && mask) dst = atomicAdd(out_counter, static_cast<uint32_t>(__popc(mask)));
+        dst = __shfl_sync(FULL, dst, 0) + static_cast<uint32_t>(__popc(mask & ((1u << lane) - 1u)));
         if (alive) {
-            q_store<2>(q.o[out] + dst, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
-            q_store<2>(q.d[out] + dst, make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u))));
-            q_store<2>(q.thr[out] + dst, make_float4(thr.x, thr.y, thr.z, pending));
+            q_store<2>(q.o_out + dst, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
+            q_store<2>(q.d_out + dst, make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u))));
+            q_store<2>(q.thr_out + dst, make_float4(thr.x, thr.y, thr.z, pending));
         }
     }
     // block-level reduction of the work counters -> one atomic per CTA and counter
@@ -532,6 +541,16 @@ __global__ void __launch_bounds__(256) k_ids_from_hits(BatchParams bp, const flo
     if (p >= bp.npix) return;
     const int32_t tri = __float_as_int(hit[p].w);
     ids[bp.pix0 + p] = tri < 0 ? -1 : static_cast<int32_t>(tris[tri].id_last & ~RT_LAST_BIT);
+}
+
+// rt_gpu_readback: packed rgb means = `res / samples` (raytracer.h:626), IEEE division like the host's
+__global__ void __launch_bounds__(256) k_means(const float4 *__restrict__ accum, float samples, uint32_t n_pixels, float *__restrict__ rgb) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    const float4 a = accum[p];
+    rgb[static_cast<size_t>(p) * 3 + 0] = __fdiv_rn(a.x, samples);
+    rgb[static_cast<size_t>(p) * 3 + 1] = __fdiv_rn(a.y, samples);
+    rgb[static_cast<size_t>(p) * 3 + 2] = __fdiv_rn(a.z, samples);
 }
 
 // Device-side Image::set_pixel (image.h:40-82): mean -> ACES -> gamma 1/2.2 -> x255 -> clamp -> round

@@ -30,6 +30,7 @@ struct PackedBvh {
     std::vector<uint32_t> order;  // BVH position -> scene.objects index
     int32_t root = RT_LINK_NONE;
     uint32_t max_depth = 0;
+    uint32_t stack_need4 = 0;     // worst-case traversal-stack entries of a ray through qnodes4 (stack_need4())
 };
 
 struct PackedScene {
@@ -305,6 +306,27 @@ inline int quantize_nodes4(const std::vector<Node4Boxes> &boxes, std::vector<QNo
         }
     });
     return rc;
+}
+
+// Worst-case number of traversal-stack entries a ray can hold in the 4-wide tree: a node step pushes every hit child but
+// the nearest (at most children - 1) and descends, so the need below a node is the sum of (children - 1) over its
+// ancestors and itself.  Both collapses number a child after its parent, so one forward pass does it.  k_extend's stack
+// holds RT_EXT_STACK_CAP entries and does not check: pack_bvh rejects a deeper tree (a degenerate chain from a host
+// builder with overlapping boxes can reach 3 entries per binary level).
+inline uint32_t stack_need4(const std::vector<QNode4> &nodes, int32_t root4, int32_t null_leaf) {
+    if (root4 < 0 || root4 == RT_LINK_NONE || nodes.empty()) return 0;
+    std::vector<uint32_t> above(nodes.size(), 0);
+    uint32_t worst = 0;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const QNode4 &q = nodes[i];
+        uint32_t n_real = 0;
+        for (int c = 0; c < 4; ++c) n_real += q.link[c] != null_leaf ? 1u : 0u;
+        const uint32_t below = above[i] + (n_real ? n_real - 1 : 0);
+        worst = std::max(worst, below);
+        for (int c = 0; c < 4; ++c)
+            if (q.link[c] >= 0 && static_cast<size_t>(q.link[c]) > i) above[q.link[c]] = below;
+    }
+    return worst;
 }
 
 // ---- 4-wide collapse straight from a tree of the library's own builder, sub-trees in parallel ------------------------
@@ -736,6 +758,7 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
     out.root = RT_LINK_NONE;
     out.root4 = RT_LINK_NONE;
     out.max_depth = 0;
+    out.stack_need4 = 0;
     out.qnodes.clear();
     out.qnodes4.clear();
     out.qnodes8.clear();
@@ -765,6 +788,8 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
         boxes.reserve(src.n_nodes / 3 + 64);
         lap.lap(1);
         out.root4 = detail::collapse4_built(src, out.tris, null_leaf, out.qnodes4, boxes);
+        out.stack_need4 = detail::stack_need4(out.qnodes4, out.root4, null_leaf);
+        if (out.stack_need4 > RT_EXT_STACK_CAP) return RT_ERR_BAD_SCENE;
         lap.lap(2);
         if (int rq = detail::quantize_nodes4(boxes, out.qnodes4)) return rq;
         lap.lap(3);
@@ -824,6 +849,8 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
         out.qnodes4.reserve(out.nodes.size() / 2 + 1);
         boxes.reserve(out.nodes.size() / 2 + 1);
         out.root4 = detail::collapse4(out.nodes, out.root, null_leaf, out.qnodes4, boxes);
+        out.stack_need4 = detail::stack_need4(out.qnodes4, out.root4, null_leaf);
+        if (out.stack_need4 > RT_EXT_STACK_CAP) return RT_ERR_BAD_SCENE;
         lap.lap(2);
         if (int rq = detail::quantize_nodes4(boxes, out.qnodes4)) return rq;
         lap.lap(3);

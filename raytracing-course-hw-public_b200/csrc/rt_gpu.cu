@@ -135,9 +135,44 @@ struct DeviceState {
     rtt::TextScene tscene;
     rt_camera tcamera;
     // render state
-    DevBuf<float4> qo[2], qd[2], qthr[2], hit, rad, accum;
-    DevBuf<float> lpdf;
+    // Path-state queues: ONE allocation, carved at fixed 2 MB-aligned offsets (round 1 used nine cudaMallocs of
+    // multi-GB arrays, whose relative placement differed from process to process).
+    DevBuf<uint8_t> arena;
+    size_t queue_cap = 0;  // paths the arena holds
+    float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr}, *qthr[2] = {nullptr, nullptr}, *hit = nullptr, *rad = nullptr;
+    float *lpdf = nullptr;
+    DevBuf<float4> accum;
+    DevBuf<float> means;   // packed rgb means (rt_gpu_readback)
     DevBuf<uint32_t> counters;
+    unsigned long long *h_stats = nullptr;  // pinned: the work counters arrive with the render's own stream sync
+    float *h_means = nullptr;               // pinned staging of the readback
+    size_t h_means_n = 0;
+    void *h_stage = nullptr;                // pinned staging of the scene upload
+    size_t h_stage_n = 0;
+    int alloc_queues(size_t cap) {
+        if (cap <= queue_cap && arena.p) return RT_OK;
+        const size_t align = size_t(2) << 20;
+        auto up = [&](size_t b) { return (b + align - 1) / align * align; };
+        const size_t b16 = up(cap * sizeof(float4)), b4 = up(cap * sizeof(float));
+        arena.release();
+        queue_cap = 0;
+        if (int rc = arena.alloc(8 * b16 + b4)) return rc;
+        uint8_t *p = arena.p;
+        if (std::getenv("RT_TIMING"))
+            std::fprintf(stderr, "rt_gpu: queue arena %p, %.1f MiB, base mod 512 MiB = %zu MiB\n", static_cast<void *>(p),
+                         (8 * b16 + b4) / 1048576.0, (reinterpret_cast<size_t>(p) >> 20) & 511);
+        auto take = [&](size_t b) { uint8_t *r = p; p += b; return r; };
+        for (int i = 0; i < 2; ++i) {
+            qo[i] = reinterpret_cast<float4 *>(take(b16));
+            qd[i] = reinterpret_cast<float4 *>(take(b16));
+            qthr[i] = reinterpret_cast<float4 *>(take(b16));
+        }
+        hit = reinterpret_cast<float4 *>(take(b16));
+        rad = reinterpret_cast<float4 *>(take(b16));
+        lpdf = reinterpret_cast<float *>(take(b4));
+        queue_cap = cap;
+        return RT_OK;
+    }
     DevBuf<unsigned long long> stats;
     DevBuf<int32_t> prim_ids;
     DevBuf<uint8_t> rgb8;
@@ -237,7 +272,7 @@ void mark(rt_gpu_ctx *ctx, DeviceState &d, int kind) {
 }
 
 // Course text scene: one launch, one thread per pixel (text_kernels.cuh).
-int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, uint32_t s_begin, uint32_t s_end,
+int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_render_params &rp, uint32_t s_begin, uint32_t s_end,
                         uint64_t &launches) {
     CU_CHECK(cudaSetDevice(d.device));
     const uint32_t W = rp.width, H = rp.height;
@@ -247,7 +282,7 @@ int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params 
     const bool ids_mode = rp.mode == RT_MODE_PRIMARY_IDS;
     if (ids_mode) {
         if (int rc = d.prim_ids.alloc(n_pix)) return rc;
-    } else if (!(rp.flags & RT_FLAG_ACCUMULATE)) {
+    } else if (!(rp.flags & RT_FLAG_ACCUMULATE) || dev_index > 0) {  // see enqueue_render
         CU_CHECK(cudaMemsetAsync(d.accum.p, 0, n_pix * sizeof(float4), d.stream));
     }
     d.marks.clear();
@@ -291,7 +326,7 @@ int enqueue_text_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params 
 }
 
 // Enqueue the whole render of samples [s_begin, s_end) on device d (asynchronous).
-int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, uint32_t s_begin, uint32_t s_end,
+int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_render_params &rp, uint32_t s_begin, uint32_t s_end,
                    uint64_t &launches) {
     CU_CHECK(cudaSetDevice(d.device));
     const uint32_t W = rp.width, H = rp.height, depth = d.scene.ray_depth;
@@ -301,7 +336,9 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
     if (int rc = d.stats.alloc(4)) return rc;
     CU_CHECK(cudaMemsetAsync(d.stats.p, 0, 4 * sizeof(unsigned long long), d.stream));
     const bool ids_mode = rp.mode == RT_MODE_PRIMARY_IDS;
-    if (!ids_mode && !(rp.flags & RT_FLAG_ACCUMULATE))
+    // RT_FLAG_ACCUMULATE keeps the sums of device 0 only: the reduce leaves the total there, while devices 1..n-1
+    // still hold their partial sums of the previous render, which the next reduce would add a second time
+    if (!ids_mode && (!(rp.flags & RT_FLAG_ACCUMULATE) || dev_index > 0))
         CU_CHECK(cudaMemsetAsync(d.accum.p, 0, n_pix * sizeof(float4), d.stream));
     d.marks.clear();
     d.events_used = 0;
@@ -331,39 +368,39 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
         max_paths = static_cast<size_t>(512) << 20;
         // the memory query is a slow, jittery driver call (tens of ms with 50 GB allocated): only when the queues
         // would have to grow beyond what this handle already holds
-        if (std::min(max_paths, want_total) > d.hit.n) {
+        if (std::min(max_paths, want_total) > d.queue_cap) {
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-                max_paths = std::min(max_paths, std::max(d.hit.n, (free_b + d.hit.n * kBytesPerPath) / 2 / kBytesPerPath));
+                max_paths = std::min(max_paths, std::max(d.queue_cap, (free_b + d.queue_cap * kBytesPerPath) / 2 / kBytesPerPath));
         }
     }
     max_paths = std::max<size_t>(max_paths, 1024);
     const size_t cap = std::min(max_paths, want_total);
-    for (int i = 0; i < 2; ++i) {
-        if (int rc = d.qo[i].alloc(cap)) return rc;
-        if (int rc = d.qd[i].alloc(cap)) return rc;
-        if (int rc = d.qthr[i].alloc(cap)) return rc;
-    }
-    if (int rc = d.hit.alloc(cap)) return rc;
-    if (int rc = d.rad.alloc(cap)) return rc;
-    if (int rc = d.lpdf.alloc(cap)) return rc;
+    if (int rc = d.alloc_queues(cap)) return rc;
     const uint32_t qdepth = std::max(depth, 1u);
-    const size_t n_counters = 3 * static_cast<size_t>(qdepth) + 1;
+    const size_t n_counters = (3 * static_cast<size_t>(qdepth) + 1) * rt::kCounterStride;  // one 256-byte line each
     if (int rc = d.counters.alloc(n_counters)) return rc;
 
-    rt::Queues q;
-    for (int i = 0; i < 2; ++i) {
-        q.o[i] = d.qo[i].p;
-        q.d[i] = d.qd[i].p;
-        q.thr[i] = d.qthr[i].p;
-    }
-    q.hit = d.hit.p;
-    q.rad = d.rad.p;
-    q.count = d.counters.p;
-    q.fetch_ext = d.counters.p + qdepth + 1;
-    q.fetch_shade = d.counters.p + 2 * qdepth + 1;
-    q.stats = d.stats.p;
-    q.lpdf = d.lpdf.p;
+    // Queues of bounce b: in = parity b & 1, out = the other one (k_generate fills queue 0 through `out` of b = -1)
+    auto queues_of = [&](int b) {
+        rt::Queues q;
+        const int in = b & 1, out = in ^ 1;
+        q.o_in = d.qo[in];
+        q.d_in = d.qd[in];
+        q.thr_in = d.qthr[in];
+        q.o_out = d.qo[out];
+        q.d_out = d.qd[out];
+        q.thr_out = d.qthr[out];
+        q.hit = d.hit;
+        q.rad = d.rad;
+        q.count = d.counters.p;
+        q.fetch_ext = d.counters.p + (qdepth + 1) * rt::kCounterStride;
+        q.fetch_shade = d.counters.p + (2 * qdepth + 1) * rt::kCounterStride;
+        q.stats = d.stats.p;
+        q.lpdf = d.lpdf;
+        return q;
+    };
+    const rt::Queues q_gen = queues_of(-1);
 
     const float inv_n_lights = d.scene.n_lights ? 1.0f / static_cast<float>(d.scene.n_lights) : 0.0f;
     rt::BatchParams bp;
@@ -385,23 +422,24 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, const rt_render_params &rp, 
             bp.k = std::min(k_max, s_end - s0);
             const uint32_t n = bp.npix * bp.k;
             CU_CHECK(cudaMemsetAsync(d.counters.p, 0, n_counters * sizeof(uint32_t), d.stream));
-            rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q);
+            rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q_gen);
             mark(ctx, d, K_GENERATE);
             if (ids_mode) {  // pixel-centre rays through the same traversal kernel, then hit -> scene.objects id
-                RT_K_EXTEND<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, 0, 0x3F800000u);
+                RT_K_EXTEND<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, queues_of(0), 0, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
-                rt::k_ids_from_hits<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.hit.p, d.scene.scene.tris, d.prim_ids.p);
+                rt::k_ids_from_hits<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.hit, d.scene.scene.tris, d.prim_ids.p);
                 mark(ctx, d, K_IDS);
                 launches += 3;
                 continue;
             }
             for (uint32_t b = 0; b < depth; ++b) {
+                const rt::Queues q = queues_of(static_cast<int>(b));
                 RT_K_EXTEND<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
                 rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b);
                 mark(ctx, d, K_SHADE);
             }
-            rt::k_accumulate<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.rad.p, d.accum.p);
+            rt::k_accumulate<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.rad, d.accum.p);
             mark(ctx, d, K_ACCUMULATE);
             launches += 2 + 2 * static_cast<uint64_t>(depth);
         }
@@ -427,17 +465,11 @@ int rt_gpu_device_count(void) {
     return n;
 }
 
-int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device) {
-    if (!out || n_gpus < 1 || first_device < 0) return fail(RT_ERR_INVALID_ARG, "rt_gpu_create: bad arguments");
-    *out = nullptr;
-    const int have = rt_gpu_device_count();
-    if (have < first_device + n_gpus)
-        return fail(RT_ERR_NO_DEVICE, "rt_gpu_create: " + std::to_string(first_device + n_gpus) +
-                                          " CUDA device(s) required, " + std::to_string(have) +
-                                          " usable (this backend has no CPU path)");
-    std::unique_ptr<rt_gpu_ctx> ctx(new rt_gpu_ctx());
+namespace {
+int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
     for (int i = 0; i < n_gpus; ++i) {
-        std::unique_ptr<DeviceState> d(new DeviceState());
+        ctx->devs.emplace_back(new DeviceState());
+        DeviceState *d = ctx->devs.back().get();
         d->device = first_device + i;
         CU_CHECK(cudaSetDevice(d->device));
         cudaDeviceProp prop;
@@ -451,53 +483,93 @@ int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device) {
         CU_CHECK(cudaEventCreate(&d->ev_end));
         CU_CHECK(cudaEventCreate(&d->ev_red0));
         CU_CHECK(cudaEventCreate(&d->ev_red1));
+        CU_CHECK(cudaMallocHost(reinterpret_cast<void **>(&d->h_stats), 4 * sizeof(unsigned long long)));
+        std::memset(d->h_stats, 0, 4 * sizeof(unsigned long long));
         int occ_e = 0, occ_s = 0;
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, RT_K_EXTEND, rt::kExtendThreads, 0));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, rt::k_shade, rt::kShadeThreads, 0));
         d->extend_blocks = d->sm_count * std::max(occ_e, 1);
         d->shade_blocks = d->sm_count * std::max(occ_s, 1);
-        ctx->devs.push_back(std::move(d));
     }
     if (n_gpus > 1) {
         if (!g_nccl.load()) return fail(RT_ERR_NCCL, "rt_gpu_create: libnccl.so.2 could not be loaded for a multi-device handle");
         std::vector<int> ids;
         for (auto &d : ctx->devs) ids.push_back(d->device);
-        ctx->comms.resize(n_gpus);
+        ctx->comms.assign(n_gpus, nullptr);
         const int rc = g_nccl.CommInitAll(ctx->comms.data(), n_gpus, ids.data());
         if (rc != 0) {
             ctx->comms.clear();
             return fail(RT_ERR_NCCL, std::string("ncclCommInitAll: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
         }
     }
-    *out = ctx.release();
+    return RT_OK;
+}
+}  // namespace
+
+int rt_gpu_create(rt_gpu_ctx **out, int n_gpus, int first_device) {
+    if (!out || n_gpus < 1 || first_device < 0) return fail(RT_ERR_INVALID_ARG, "rt_gpu_create: bad arguments");
+    *out = nullptr;
+    const int have = rt_gpu_device_count();
+    if (have < first_device + n_gpus)
+        return fail(RT_ERR_NO_DEVICE, "rt_gpu_create: " + std::to_string(first_device + n_gpus) +
+                                          " CUDA device(s) required, " + std::to_string(have) +
+                                          " usable (this backend has no CPU path)");
+    rt_gpu_ctx *ctx = new rt_gpu_ctx();
+    if (int rc = create_devices(ctx, n_gpus, first_device)) {
+        const std::string why = g_last_error;
+        rt_gpu_destroy(ctx);  // streams, events, pinned memory and communicators built so far
+        g_last_error = why;
+        return rc;
+    }
+    *out = ctx;
     return RT_OK;
 }
 
 void rt_gpu_destroy(rt_gpu_ctx *ctx) {
     if (!ctx) return;
-    for (ncclComm_t c : ctx->comms) g_nccl.CommDestroy(c);
+    // also the cleanup of a partially constructed handle (rt_gpu_create's error paths): every member may be null
+    for (auto &dp : ctx->devs) {  // the device work (incl. a reduce in flight) ends before the communicators go
+        if (!dp || !dp->stream) continue;
+        cudaSetDevice(dp->device);
+        cudaStreamSynchronize(dp->stream);
+    }
+    for (ncclComm_t c : ctx->comms)
+        if (c) g_nccl.CommDestroy(c);
     for (auto &dp : ctx->devs) {
+        if (!dp) continue;
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
-        cudaStreamSynchronize(d.stream);
-        d.qnodes4.release(); d.lqnodes4.release(); d.qnodes8.release(); d.lqnodes8.release(); d.lpdf.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
+        d.qnodes4.release(); d.lqnodes4.release(); d.qnodes8.release(); d.lqnodes8.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
-        for (int i = 0; i < 2; ++i) { d.qo[i].release(); d.qd[i].release(); d.qthr[i].release(); }
-        d.hit.release(); d.rad.release(); d.accum.release(); d.counters.release(); d.stats.release();
+        d.arena.release(); d.means.release(); d.accum.release();
+        if (d.h_stats) cudaFreeHost(d.h_stats);
+        if (d.h_means) cudaFreeHost(d.h_means);
+        if (d.h_stage) cudaFreeHost(d.h_stage);
+        d.counters.release(); d.stats.release();
         d.prim_ids.release(); d.rgb8.release();
         for (cudaEvent_t e : d.event_pool) cudaEventDestroy(e);
-        cudaEventDestroy(d.ev_begin); cudaEventDestroy(d.ev_end);
-        cudaEventDestroy(d.ev_red0); cudaEventDestroy(d.ev_red1);
-        cudaStreamDestroy(d.stream);
+        for (cudaEvent_t e : {d.ev_begin, d.ev_end, d.ev_red0, d.ev_red1})
+            if (e) cudaEventDestroy(e);
+        if (d.stream) cudaStreamDestroy(d.stream);
     }
+    cudaGetLastError();
     delete ctx;
 }
 
 int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     if (!ctx || !scene) return fail(RT_ERR_INVALID_ARG, "rt_gpu_upload_scene: null argument");
     if (scene->abi_version != RT_GPU_ABI_VERSION) return fail(RT_ERR_INVALID_ARG, "rt_gpu_upload_scene: ABI version mismatch");
-    // structural validation (ids in range) before anything is dereferenced on the device
+    // structural validation (ids in range, arrays present) before anything is dereferenced
+    if (scene->n_tris > 0 && (!scene->tri_pos || !scene->tri_normals || !scene->tri_uv || !scene->tri_material))
+        return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_scene: null per-triangle array with n_tris > 0");
+    if ((scene->n_materials > 0 && !scene->materials) || (scene->n_textures > 0 && !scene->textures) ||
+        (scene->texel_bytes > 0 && !scene->texels))
+        return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_scene: null material / texture array");
+    if (scene->env_texture > scene->n_textures) return fail(RT_ERR_BAD_SCENE, "environment texture id out of range");
+    for (const rt_bvh_desc *b : {&scene->scene_bvh, &scene->light_bvh})
+        if ((b->n_nodes > 0 && !b->nodes) || (b->n_objects > 0 && !b->objects))
+            return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_scene: null BVH array");
     for (uint32_t i = 0; i < scene->n_tris; ++i)
         if (scene->tri_material[i] >= scene->n_materials) return fail(RT_ERR_BAD_SCENE, "material id out of range");
     for (const rt_bvh_desc *b : {&scene->scene_bvh, &scene->light_bvh}) {
@@ -531,7 +603,7 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     struct ResetTimes {
         ~ResetTimes() { rt::pack_times() = nullptr; }
     } reset_times;
-    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : rt::RT_PACK_Q4)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects or depth > 64)");
+    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : rt::RT_PACK_Q4)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects, depth > 64, non-finite box, or a 4-wide tree whose traversal needs more than RT_EXT_STACK_CAP stack entries)");
     const auto t_pack1 = std::chrono::steady_clock::now();
     for (auto &d : ctx->devs)
         if (int rc = upload_to_device(*d, *scene, packed)) return rc;
@@ -627,11 +699,14 @@ int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params) {
             if (local.pixel_end == local.pixel_begin) se = sb;  // nothing for this device: zero buffer only
         }
         if (rp.mode == RT_MODE_PRIMARY_IDS && g > 0) continue;  // ids: device 0 only
+        DeviceState &dg = *ctx->devs[g];
         if (ctx->text_scene) {
-            if (int rc = enqueue_text_render(ctx, *ctx->devs[g], local, sb, se, launches)) return rc;
-        } else if (int rc = enqueue_render(ctx, *ctx->devs[g], local, sb, se, launches)) {
+            if (int rc = enqueue_text_render(ctx, dg, g, local, sb, se, launches)) return rc;
+        } else if (int rc = enqueue_render(ctx, dg, g, local, sb, se, launches)) {
             return rc;
         }
+        // the work counters travel on the stream into pinned memory: no second synchronising copy after the render
+        CU_CHECK(cudaMemcpyAsync(dg.h_stats, dg.stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dg.stream));
     }
     const size_t n_floats = static_cast<size_t>(rp.width) * rp.height * 4;
     if (n > 1 && rp.mode == RT_MODE_BEAUTY) {
@@ -668,8 +743,7 @@ int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params) {
             CU_CHECK(cudaEventElapsedTime(&ms, d.ev_red0, d.ev_red1));
             st.reduce_ms = std::max(st.reduce_ms, static_cast<double>(ms));
         }
-        unsigned long long hs[4] = {0, 0, 0, 0};
-        if (d.stats.p) CU_CHECK(cudaMemcpy(hs, d.stats.p, sizeof hs, cudaMemcpyDeviceToHost));
+        const unsigned long long *hs = d.h_stats;
         st.extension_rays += hs[0];
         st.light_pdf_rays += hs[1];
         st.shades += hs[2];
@@ -699,13 +773,41 @@ int rt_gpu_readback(rt_gpu_ctx *ctx, float *rgb_mean, int32_t *prim_ids, rt_stat
     const size_t n_pix = static_cast<size_t>(ctx->last.width) * ctx->last.height;
     if (rgb_mean) {
         if (ctx->last.mode != RT_MODE_BEAUTY) return fail(RT_ERR_NO_RENDER, "rt_gpu_readback: last render was not a beauty render");
-        std::vector<float4> host(n_pix);
-        CU_CHECK(cudaMemcpy(host.data(), d.accum.p, n_pix * sizeof(float4), cudaMemcpyDeviceToHost));
-        const float samples = static_cast<float>(ctx->last.samples);
-        for (size_t i = 0; i < n_pix; ++i) {  // `res / samples`, raytracer.h:626
-            rgb_mean[i * 3 + 0] = host[i].x / samples;
-            rgb_mean[i * 3 + 1] = host[i].y / samples;
-            rgb_mean[i * 3 + 2] = host[i].z / samples;
+        // the division and the float4 -> rgb packing run on the device (12 B per pixel cross the bus instead of 16);
+        // the copy lands directly in the caller's buffer when that is pinned, else in chunks through a persistent
+        // pinned staging buffer, each chunk's host memcpy overlapping the next chunk's DMA
+        const size_t n_f = n_pix * 3;
+        if (int rc = d.means.alloc(n_f)) return rc;
+        const uint32_t np32 = static_cast<uint32_t>(n_pix);
+        rt::k_means<<<(np32 + 255) / 256, 256, 0, d.stream>>>(d.accum.p, static_cast<float>(ctx->last.samples), np32, d.means.p);
+        CU_CHECK(cudaGetLastError());
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, rgb_mean) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) {
+            CU_CHECK(cudaMemcpyAsync(rgb_mean, d.means.p, n_f * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
+            CU_CHECK(cudaStreamSynchronize(d.stream));
+        } else {
+            if (d.h_means_n < n_f) {
+                if (d.h_means) cudaFreeHost(d.h_means);
+                d.h_means = nullptr;
+                d.h_means_n = 0;
+                CU_CHECK(cudaMallocHost(reinterpret_cast<void **>(&d.h_means), n_f * sizeof(float)));
+                d.h_means_n = n_f;
+            }
+            constexpr int kChunks = 4;
+            size_t at[kChunks + 1];
+            for (int c = 0; c <= kChunks; ++c) at[c] = n_f * c / kChunks;
+            for (int c = 0; c < kChunks; ++c) {
+                CU_CHECK(cudaMemcpyAsync(d.h_means + at[c], d.means.p + at[c], (at[c + 1] - at[c]) * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
+                CU_CHECK(cudaEventRecord(c & 1 ? d.ev_red1 : d.ev_red0, d.stream));
+                if (c > 0) {
+                    CU_CHECK(cudaEventSynchronize((c - 1) & 1 ? d.ev_red1 : d.ev_red0));
+                    std::memcpy(rgb_mean + at[c - 1], d.h_means + at[c - 1], (at[c] - at[c - 1]) * sizeof(float));
+                }
+            }
+            CU_CHECK(cudaStreamSynchronize(d.stream));
+            std::memcpy(rgb_mean + at[kChunks - 1], d.h_means + at[kChunks - 1], (at[kChunks] - at[kChunks - 1]) * sizeof(float));
         }
     }
     if (prim_ids) {

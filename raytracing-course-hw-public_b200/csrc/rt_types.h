@@ -27,6 +27,8 @@
 
 #define RT_STACK_SIZE 64        /* BVH::build max_depth = 64, bvh.h:371 */
 #define RT_LINK_NONE 0x7FFFFFFF /* empty BVH */
+#define RT_EXT_STACK_CAP 96     /* traversal-stack entries per ray in k_extend (shared + local part); the upload rejects a
+                                   4-wide tree whose worst-case need (repack.h, stack_need4) exceeds it */
 #define RT_LAST_BIT 0x80000000u
 
 struct alignas(64) DNode {

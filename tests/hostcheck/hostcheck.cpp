@@ -72,6 +72,17 @@ extern "C" {
 void hc_set_rebuild(int on) { g_rebuild = on != 0; }
 void hc_set_wide8(int on) { g_wide8 = on != 0; }
 
+// Worst-case k_extend stack entries of the packed 4-wide trees (out[0] scene, out[1] light); the return value is
+// pack_scene's: RT_ERR_BAD_SCENE when a tree needs more than RT_EXT_STACK_CAP
+int hc_stack_need(const rt_scene_desc *sc, double *out) {
+    HostScene hs;
+    const int rc = pack_scene(*sc, hs.p, g_rebuild, g_rebuild ? RT_PACK_Q4 : RT_PACK_ALL);
+    out[0] = (double)hs.p.scene.stack_need4;
+    out[1] = (double)hs.p.light.stack_need4;
+    out[2] = (double)RT_EXT_STACK_CAP;
+    return rc;
+}
+
 // Primary ids through the upload path's own packing: library-built tree + direct parallel 4-wide collapse
 // (pack_bvh's built_tree fast path, formats = RT_PACK_Q4 only); out[0] = wide nodes, out[1] = node steps per ray
 int hc_primary_ids_upload_path(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids, double *out) {

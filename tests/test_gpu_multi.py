@@ -57,6 +57,28 @@ def test_single_process_multi_device_matches_one_device(golden_scene):
     assert np.allclose(img1, ref1, rtol=2e-6, atol=1e-7)
 
 
+@needs2
+def test_accumulate_on_a_multi_device_handle(golden_scene):
+    """RT_FLAG_ACCUMULATE with n_gpus > 1: the reduce leaves the total on device 0 while the other
+    devices keep their partial sums, which a second accumulating render must not add again — two half renders
+    equal one full render."""
+    sc = golden_scene("small_lights")
+    w, h, spp = 96, 64, 32
+    n = min(_n_dev(), 8)
+    with gpu.RtGpu(n, 0) as many:
+        many.upload_scene(sc)
+        many.render(w, h, spp, seed=11)
+        full, _ = many.readback()
+        many.render(w, h, spp, seed=11, sample_begin=0, sample_end=spp // 2)
+        many.render(w, h, spp, seed=11, sample_begin=spp // 2, sample_end=spp, accumulate=True)
+        halves, _ = many.readback()
+        # and a third accumulating pass of zero samples changes nothing
+        many.render(w, h, spp, seed=11, sample_begin=spp, sample_end=spp, accumulate=True)
+        again, _ = many.readback()
+    assert np.allclose(halves, full, rtol=2e-6, atol=1e-7)
+    assert np.array_equal(again, halves)
+
+
 _RANK_SCRIPT = r"""
 import os, sys
 sys.path[:0] = [{root!r}, os.path.join({root!r}, "tests")]

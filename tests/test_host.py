@@ -360,6 +360,70 @@ def test_eight_wide_collapse_on_the_260k_scene(hc, big_scene):
     assert out[2] * 96 * 96 < 0.8 * steps[0]  # fewer node steps than the 4-wide traversal of the same rays
 
 
+def _comb_scene(levels, r=0.97):
+    """Adversarial host tree: a comb N_k = (S_k, N_k+1) whose side branch S_k = (T, T') is larger than the
+    rest of the chain, so the 4-wide collapse opens S_k and T and leaves N_k+1 one BINARY level below its wide
+    parent: every wide node on the chain has four children (three pushes) and the wide depth equals the chain length."""
+    tris, nodes = [], []
+
+    def leaf(size, z):
+        tris.append([[-size, -size, z], [size, -size, z], [0, size, z]])
+        nodes.append(dict(lo=[-size, -size, z], hi=[size, size, z], l=_abi.RT_NO_CHILD, r=_abi.RT_NO_CHILD,
+                          b=len(tris) - 1, e=len(tris)))
+        return len(nodes) - 1
+
+    def inner(make_l, make_r):
+        i = len(nodes)
+        nodes.append(None)
+        l, rr = make_l(), make_r()
+        lo = np.minimum(nodes[l]["lo"], nodes[rr]["lo"])
+        hi = np.maximum(nodes[l]["hi"], nodes[rr]["hi"])
+        nodes[i] = dict(lo=lo, hi=hi, l=l, r=rr, b=0, e=0)
+        return i
+
+    def chain(k):
+        size, z = r ** k, 0.001 * k
+        if k == levels:
+            return leaf(size, z)
+        pair = lambda dz: (lambda: inner(lambda: leaf(size, z + dz), lambda: leaf(size * 0.999, z + dz + 1e-4)))
+        return inner(lambda: inner(pair(2e-4), pair(4e-4)), lambda: chain(k + 1))
+
+    root = chain(0)
+    arr = np.zeros(len(nodes), _abi.NODE_DTYPE)
+    for i, nd in enumerate(nodes):
+        arr[i] = (nd["lo"], nd["hi"], nd["l"], nd["r"], nd["b"], nd["e"])
+    n = len(tris)
+    sc = rt_b200.SceneData.load(os.path.join(GOLDEN, "tiny.rtsc"))
+    sc.tri_pos = np.array(tris, np.float32)
+    sc.tri_normals = np.tile(np.array([0, 0, 1], np.float32), (n, 3, 1))
+    sc.tri_uv = np.zeros((n, 3, 2), np.float32)
+    sc.tri_tangents = None
+    sc.tri_material = np.zeros(n, np.uint32)
+    sc.scene_bvh = _abi.BvhData(arr, np.arange(n, dtype=np.uint32), root)
+    sc.light_bvh = _abi.BvhData(np.zeros(0, _abi.NODE_DTYPE), np.zeros(0, np.uint32), _abi.RT_NO_CHILD)
+    return sc
+
+
+def test_traversal_stack_bound_is_enforced_at_upload(hc, big_scene, golden_scene):
+    """k_extend's per-ray stack holds RT_EXT_STACK_CAP entries without a bounds check; the packer computes the exact
+    worst case of the collapsed tree and rejects what does not fit (a host tree may be 64 levels deep, bvh.h:371)."""
+    out = np.zeros(3)
+    hc.hc_set_rebuild(0)
+    d = _comb_scene(30).desc()  # 30 chain levels x 3 pushes: fits
+    assert hc.hc_stack_need(C.byref(d), out.ctypes.data_as(C.c_void_p)) == 0
+    assert 85 <= out[0] <= out[2] == 96, out
+    d = _comb_scene(58).desc()  # 61 binary levels (bvh.h:371 allows 64): three entries per level do not fit
+    assert hc.hc_stack_need(C.byref(d), out.ctypes.data_as(C.c_void_p)) == -7  # RT_ERR_BAD_SCENE
+    assert out[0] > 120, out
+    hc.hc_set_rebuild(1)  # the library's own builder on the bench scene: far below the capacity
+    d = big_scene.desc()
+    assert hc.hc_stack_need(C.byref(d), out.ctypes.data_as(C.c_void_p)) == 0
+    assert 0 < out[0] <= 64, out
+    hc.hc_set_rebuild(0)
+    d = golden_scene("small_lights").desc()
+    assert hc.hc_stack_need(C.byref(d), out.ctypes.data_as(C.c_void_p)) == 0 and out[1] > 0
+
+
 def test_device_philox_matches_known_answers(hc):
     out = (C.c_uint32 * 4)()
     hc.hc_philox((C.c_uint32 * 4)(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344),
