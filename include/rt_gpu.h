@@ -130,8 +130,12 @@ typedef struct rt_scene_desc {
     const rt_material *materials;
     const rt_texture *textures;
     const uint8_t *texels;
-    rt_bvh_desc scene_bvh;         /* over all triangles (raytracer.h:441-443) */
-    rt_bvh_desc light_bvh;         /* over emission != 0 (raytracer.h:444-447) */
+    rt_bvh_desc scene_bvh;         /* over all triangles (raytracer.h:441-443).  OPTIONAL: n_nodes == 0 (root RT_NO_CHILD,
+                                      no arrays) leaves the build to the library, which rebuilds the tree anyway unless
+                                      RT_SCENE_KEEP_HOST_BVH is set — a host then skips its own scene-BVH build
+                                      (0.85 s for 260k triangles with the reference's builder, bvh.h:262-393) */
+    rt_bvh_desc light_bvh;         /* over emission != 0 (raytracer.h:444-447): REQUIRED when the scene has emitters — its
+                                      object order is the order bvh_mix_dist::sample indexes (raytracer.h:355-361) */
 } rt_scene_desc;
 
 /* rt_scene_desc.flags */

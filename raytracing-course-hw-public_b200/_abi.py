@@ -158,6 +158,14 @@ class SceneData:
         self.textures = np.ascontiguousarray(self.textures, TEXTURE_DTYPE)
         self.texels = np.ascontiguousarray(self.texels, np.uint8)
 
+    def without_scene_bvh(self):
+        """Shallow copy that passes no scene BVH (rt_gpu.h: scene_bvh.n_nodes == 0 -> the library builds it)."""
+        import copy
+
+        s = copy.copy(self)
+        s.scene_bvh = BvhData(np.zeros(0, NODE_DTYPE), np.zeros(0, np.uint32), RT_NO_CHILD)
+        return s
+
     def desc(self):
         """ctypes rt_scene_desc aliasing this object's arrays (keep `self` alive while it is used)."""
         self._normalise()

@@ -860,9 +860,16 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
 
 // `rebuild_scene_bvh`: build the scene BVH with the library's SAH builder (sah_build.h) over the triangles of
 // sc.scene_bvh instead of adopting the host's tree; the light BVH is always adopted as passed.
+// A host that passes NO scene BVH (scene_bvh.n_nodes == 0; rt_gpu.h) leaves the build to the library: the tree is built
+// over all n_tris triangles in scene.objects order.
 inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false, int formats = RT_PACK_ALL) {
     PackLap lap;
-    if (rebuild_scene_bvh && sc.scene_bvh.n_objects > 0 && sc.scene_bvh.root != RT_NO_CHILD) {
+    const bool no_host_tree = sc.scene_bvh.n_nodes == 0 && sc.n_tris > 0;
+    if (no_host_tree) {
+        build_sah_bvh(sc.tri_pos, nullptr, sc.n_tris, out.built, &out.sah_scratch);
+        lap.lap(0);
+        if (int rc = pack_bvh(sc, out.built.desc(), out.scene, formats, true)) return rc;
+    } else if (rebuild_scene_bvh && sc.scene_bvh.n_objects > 0 && sc.scene_bvh.root != RT_NO_CHILD) {
         build_sah_bvh(sc.tri_pos, sc.scene_bvh.objects, sc.scene_bvh.n_objects, out.built, &out.sah_scratch);
         lap.lap(0);
         if (int rc = pack_bvh(sc, out.built.desc(), out.scene, formats, true)) return rc;

@@ -597,6 +597,8 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     rt::PackedScene &packed = ctx->packed;
     const char *keep_env = std::getenv("RT_KEEP_HOST_BVH");  // A/B switch for measurements
     const bool keep = (scene->flags & RT_SCENE_KEEP_HOST_BVH) || (keep_env && std::atoi(keep_env) != 0);
+    if ((scene->flags & RT_SCENE_KEEP_HOST_BVH) && scene->scene_bvh.n_nodes == 0 && scene->n_tris > 0)
+        return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_scene: RT_SCENE_KEEP_HOST_BVH without a scene BVH");
     const auto t_pack0 = std::chrono::steady_clock::now();
     double phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     rt::pack_times() = std::getenv("RT_TIMING") ? phase : nullptr;

@@ -58,8 +58,9 @@ inline rt_bvh_desc flatten_bvh(const Scene &scene, const BVH &bvh, std::vector<u
     return d;
 }
 
-// `ctx` must outlive the returned FlatScene (BVH nodes are referenced, not copied).
-inline void flatten(const Scene &scene, const RaytracerStaticContext &ctx, FlatScene &out) {
+// `scene_bvh` (may be null: the library then builds the scene BVH itself) and `light_bvh` must outlive the returned
+// FlatScene (BVH nodes are referenced, not copied).
+inline void flatten(const Scene &scene, const BVH *scene_bvh, const BVH &light_bvh, FlatScene &out) {
     const size_t n = scene.objects.size();
     out.tri_pos.resize(n * 9);
     out.tri_normals.resize(n * 9);
@@ -160,8 +161,24 @@ inline void flatten(const Scene &scene, const RaytracerStaticContext &ctx, FlatS
     d.materials = out.materials.data();
     d.textures = out.textures.data();
     d.texels = out.texels.data();
-    d.scene_bvh = flatten_bvh(scene, ctx.scene_bvh, out.scene_objects);
-    d.light_bvh = flatten_bvh(scene, ctx.light_bvh, out.light_objects);
+    if (scene_bvh) {
+        d.scene_bvh = flatten_bvh(scene, *scene_bvh, out.scene_objects);
+    } else {
+        std::memset(&d.scene_bvh, 0, sizeof d.scene_bvh);
+        d.scene_bvh.root = RT_NO_CHILD;
+    }
+    d.light_bvh = flatten_bvh(scene, light_bvh, out.light_objects);
+}
+
+// The reference's own context (both trees built by RaytracerStaticContext, raytracer.h:440-447).
+inline void flatten(const Scene &scene, const RaytracerStaticContext &ctx, FlatScene &out) {
+    flatten(scene, &ctx.scene_bvh, ctx.light_bvh, out);
+}
+
+// raytracer.h:444-447 alone: the light BVH, whose object order the light sampler indexes.
+inline BVH build_light_bvh(const Scene &scene) {
+    return BVH::build(std::span(scene.objects),
+                      [](const geometry::Object &obj) { return obj.material.emission != geometry::color3{0, 0, 0}; });
 }
 
 }  // namespace rt_flatten

@@ -2,14 +2,15 @@
 //
 // Same five positional arguments, same exit codes and the same output file as the reference CLI
 // (src/main.cpp:16-49).  Everything on the host is the reference's own code, used through its headers
-// (-I<reference>/src, never copied): parse_gltf_scene (scene.h:183), both BVH::build calls inside
-// RaytracerStaticContext (raytracer.h:440-447), Image::set_pixel's tonemap / gamma / quantisation
+// (-I<reference>/src, never copied): parse_gltf_scene (scene.h:183), the light-BVH build of
+// RaytracerStaticContext (raytracer.h:444-447), Image::set_pixel's tonemap / gamma / quantisation
 // (image.h:40-82) and Image::write (image.h:34).  The only replaced call is run_raytracer(scene, img)
 // (main.cpp:37): the per-pixel Monte-Carlo loop runs on the B200(s) through the rt_gpu C ABI.
 //
 // Optional environment (additions; the 5-argument form needs none of them):
 //   RT_GPUS   number of GPUs of this box to split the samples over (default 1)
 //   RT_SEED   Philox seed (default 0)
+//   RT_HOST_SCENE_BVH  1: also build the reference's scene BVH and pass it (default: the library builds its own)
 //   RT_ENV_MAP  image file used as the equirectangular environment map Scene::bg (the run-time form of the
 //             reference's compile-time USE_ENV_MAP / ENV_MAP_PATH, src/config.h:35-37)
 #define STB_IMAGE_IMPLEMENTATION
@@ -19,6 +20,7 @@
 #include <filesystem>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 #include <vector>
 
@@ -60,9 +62,22 @@ int main(int argc, char **argv) try {
     Image img(width, height, scene.bg_color);
 
     if (scene.ray_depth != 0) {  // run_raytracer's early-out, raytracer.h:630
-        RaytracerStaticContext ctx(scene);  // host-side BVH builds stay the reference's
+        // Host-side BVH builds stay the reference's code, but only the light BVH is needed: its object order is what
+        // bvh_mix_dist::sample indexes (raytracer.h:355-361).  The scene BVH the GPU traverses is the library's own
+        // (include/rt_gpu.h: scene_bvh.n_nodes == 0), so the reference's 0.85 s scene build (260k triangles) is skipped
+        // unless RT_HOST_SCENE_BVH=1 asks for the reference's tree to be built and passed (RT_KEEP_HOST_BVH=1 makes the
+        // library traverse it as is).
+        const bool host_tree = env_uint("RT_HOST_SCENE_BVH", 0) != 0;
+        std::unique_ptr<RaytracerStaticContext> ctx;
+        BVH light_only;
         rt_flatten::FlatScene flat;
-        rt_flatten::flatten(scene, ctx, flat);
+        if (host_tree) {
+            ctx.reset(new RaytracerStaticContext(scene));
+            rt_flatten::flatten(scene, *ctx, flat);
+        } else {
+            light_only = rt_flatten::build_light_bvh(scene);
+            rt_flatten::flatten(scene, nullptr, light_only, flat);
+        }
 
         rt_gpu_ctx *gpu = nullptr;
         check(rt_gpu_create(&gpu, static_cast<int>(env_uint("RT_GPUS", 1)), 0), "rt_gpu_create");

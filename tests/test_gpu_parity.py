@@ -47,6 +47,26 @@ def test_primary_ids_big_scene(rt, manifest, big_scene):
     assert (ids == ref).mean() >= 0.999
 
 
+def test_upload_without_host_scene_bvh(rt, manifest, golden_scene, big_scene):
+    """scene_bvh.n_nodes == 0: the library builds the tree itself; ids and images are those of the upload that
+    passes the host's tree (closest hits do not depend on the tree)."""
+    for sc, (w, h) in ((golden_scene("small_lights"), (96, 64)), (big_scene, (256, 256))):
+        rt.upload_scene(sc)
+        ids_a = rt.primary_ids(w, h)
+        rt.render(w, h, 8, seed=3)
+        img_a, _ = rt.readback()
+        rt.upload_scene(sc.without_scene_bvh())
+        ids_b = rt.primary_ids(w, h)
+        rt.render(w, h, 8, seed=3)
+        img_b, _ = rt.readback()
+        assert (ids_a == ids_b).mean() >= 0.9999
+        rel = np.abs(img_a - img_b) / (np.abs(img_a) + 1e-3)
+        assert (rel.max(axis=2) > 1e-3).mean() <= 0.01
+    d = golden_scene("tiny").without_scene_bvh().desc()
+    d.flags = 1  # RT_SCENE_KEEP_HOST_BVH without a tree
+    assert gpu.lib().rt_gpu_upload_scene(rt._h, d) == -7
+
+
 @pytest.mark.parametrize("name,tol_frac", [("tiny", 0.02), ("small_lights", 0.08), ("texall", 0.6), ("tiny_env", 0.02)])
 def test_paths_follow_oracle(name, tol_frac, rt, manifest, golden_scene):
     """Same Philox keys -> same paths. texall contains alpha = 0.0016 near-mirrors whose GGX D term is

@@ -325,6 +325,24 @@ def test_upload_path_packing_gives_reference_ids(name, hc, manifest, golden_scen
     assert (ids == ref).mean() >= 0.999
 
 
+@pytest.mark.parametrize("name", SMALL)
+def test_scene_without_host_bvh_is_built_by_the_library(name, hc, manifest, golden_scene):
+    """rt_scene_desc.scene_bvh is optional (n_nodes == 0): the library builds the tree over all triangles in
+    scene.objects order, so a host can skip BVH::build (bvh.h:262-393) for the scene."""
+    m = manifest["scenes"][name]
+    w, h = m["width"], m["height"]
+    d = golden_scene(name).without_scene_bvh().desc()
+    assert d.scene_bvh.n_nodes == 0 and d.scene_bvh.n_objects == 0
+    ids = np.zeros((h, w), np.int32)
+    out = (C.c_double * 2)()
+    assert hc.hc_primary_ids_upload_path(C.byref(d), w, h, ids.ctypes.data_as(C.c_void_p), out) == 0
+    ref = golden_array(f"{name}_ids.i32", np.int32, (h, w))
+    assert (ids == ref).mean() >= 0.999 and out[0] > 0
+    res = np.zeros(8)
+    assert hc.hc_wide_containment(C.byref(d), 4, 1, res.ctypes.data_as(C.c_void_p)) == 0
+    assert res[0] > 0 and res[1] == 0 and res[2] >= golden_scene(name).n_tris  # planes checked, none violated, every triangle reached
+
+
 def test_upload_path_packing_on_the_260k_scene(hc, big_scene):
     """Same wide tree as the serial collapse over the binary node array: same number of nodes, same node steps, same ids."""
     d = big_scene.desc()
