@@ -262,6 +262,14 @@ int rt_gpu_accum_device_ptr(rt_gpu_ctx *ctx, void **dptr, size_t *n_floats);
  * rgb8 = width*height*3 bytes, ready to follow the "P6" header. */
 int rt_gpu_readback_rgb8(rt_gpu_ctx *ctx, uint8_t *rgb8);
 
+/* Diagnostic (tests): the scene BVH the library built on the device during the last rt_gpu_upload_scene.
+ * which = 0: uint32[8] {n_tris, binary node slots, 4-wide nodes, root link, worst-case traversal stack need, depth of
+ * the binary tree, 1 if built on the device, levels of the top-down phase}; 1: rt_bvh_node[slots] (the binary tree in the
+ * slot layout left = i + 1, right = i + 2 * n_left; unused slots are undefined); 2: uint32[n_tris] scene.objects id at
+ * each BVH position; 3: the 4-wide quantised nodes (64 B each); 4: the device triangles (64 B each, n_tris + 1).
+ * dst == NULL only reports the size in *bytes.  Selectors 1..4 are empty when the host built the tree. */
+int rt_gpu_debug_get_bvh(rt_gpu_ctx *ctx, int which, void *dst, size_t *bytes);
+
 /* Per-kernel timing (serialises launches with events; off by default). */
 int rt_gpu_set_profiling(rt_gpu_ctx *ctx, int enable);
 

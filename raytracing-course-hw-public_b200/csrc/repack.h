@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "quantize.h"
 #include "rt_gpu.h"
 #include "rt_types.h"
 #include "sah_build.h"
@@ -144,67 +145,6 @@ inline int32_t pack_node(const rt_bvh_desc &src, uint32_t ref_id, PackedBvh &out
     return idx;
 }
 
-inline uint32_t fbits(float f) {
-    uint32_t u;
-    std::memcpy(&u, &f, 4);
-    return u;
-}
-inline float bitsf(uint32_t u) {
-    float f;
-    std::memcpy(&f, &u, 4);
-    return f;
-}
-
-// One axis of a QNode: grid word (origin bits | cell exponent) and the four plane bytes
-// (left lo, left hi, right lo, right hi).  Conservative in exact arithmetic with a margin of 1/64 cell
-// for the device's ray-space rounding (pt_core.cuh, qnode_axis()).  Returns false when the extent
-// cannot be represented (non-finite box).
-inline bool quantize_axis_n(const float *lo, const float *hi, int n, uint32_t &word, uint8_t *qlo, uint8_t *qhi) {
-    float mn = lo[0], mx = hi[0];
-    for (int c = 1; c < n; ++c) {
-        mn = lo[c] < mn ? lo[c] : mn;
-        mx = hi[c] > mx ? hi[c] : mx;
-    }
-    if (!(std::isfinite(mn) && std::isfinite(mx)) || mx < mn) return false;
-    const double margin = 1.0 / 64.0;
-    const double ext = static_cast<double>(mx) - static_cast<double>(mn);
-    int e_first = 1;
-    if (ext > 0.0) e_first = std::max(1, std::ilogb(ext / 255.0) + 127 - 1);
-    for (int e = e_first; e <= 238; ++e) {  // smallest cell that covers the extent in 255 steps (e + 16 stays a finite exponent)
-        const double cell = std::ldexp(1.0, e - 127);
-        const uint32_t eb = static_cast<uint32_t>(e);
-        // origin = the float whose bits are (23 high bits chosen here | bit 8 = 0 | e); it has to be
-        // <= mn - margin * cell.  Round that target down to a float, then down to the representable words.
-        const double target = static_cast<double>(mn) - margin * cell;
-        float tf = static_cast<float>(target);
-        if (static_cast<double>(tf) > target) tf = std::nextafterf(tf, -std::numeric_limits<float>::infinity());
-        uint32_t w;
-        if (tf > 0.0f) {
-            const uint32_t tb = fbits(tf);
-            w = (tb & ~0x1FFu) | eb;
-            if (w > tb) w = (tb & ~0x1FFu) >= 0x200u ? w - 0x200u : (0x80000000u | eb);
-        } else {  // negative (or zero): more magnitude = smaller value
-            const uint32_t tb = tf == 0.0f ? 0x80000000u : fbits(tf);
-            w = (tb & ~0x1FFu) | eb;
-            if (w < tb) w += 0x200u;
-        }
-        const double org = static_cast<double>(bitsf(w));
-        if (!std::isfinite(org) || !(org <= target)) continue;
-        const double top = (static_cast<double>(mx) - org) / cell + margin;
-        if (top > 255.0) continue;
-        word = w;
-        for (int c = 0; c < n; ++c) {
-            double a = std::floor((static_cast<double>(lo[c]) - org) / cell - margin);
-            double z = std::ceil((static_cast<double>(hi[c]) - org) / cell + margin);
-            if (a < 0.0) a = 0.0;  // cannot happen: org <= mn - margin * cell
-            if (z > 255.0) z = 255.0;
-            qlo[c] = static_cast<uint8_t>(a);
-            qhi[c] = static_cast<uint8_t>(z);
-        }
-        return true;
-    }
-    return false;
-}
 inline bool quantize_axis(const float lo[2], const float hi[2], uint32_t &word, uint8_t q[4]) {
     uint8_t ql[2], qh[2];
     if (!quantize_axis_n(lo, hi, 2, word, ql, qh)) return false;
@@ -862,10 +802,15 @@ inline int pack_bvh(const rt_scene_desc &sc, const rt_bvh_desc &src, PackedBvh &
 // sc.scene_bvh instead of adopting the host's tree; the light BVH is always adopted as passed.
 // A host that passes NO scene BVH (scene_bvh.n_nodes == 0; rt_gpu.h) leaves the build to the library: the tree is built
 // over all n_tris triangles in scene.objects order.
-inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false, int formats = RT_PACK_ALL) {
+// `with_scene` = false: only the small host-side parts (light BVH, sampling list, materials, textures, LUT); the scene BVH,
+// triangles and attributes are then produced on the device (gpu_build.cuh).
+inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_scene_bvh = false, int formats = RT_PACK_ALL,
+                      bool with_scene = true) {
     PackLap lap;
     const bool no_host_tree = sc.scene_bvh.n_nodes == 0 && sc.n_tris > 0;
-    if (no_host_tree) {
+    if (!with_scene) {
+        out.scene = PackedBvh();
+    } else if (no_host_tree) {
         build_sah_bvh(sc.tri_pos, nullptr, sc.n_tris, out.built, &out.sah_scratch);
         lap.lap(0);
         if (int rc = pack_bvh(sc, out.built.desc(), out.scene, formats, true)) return rc;
@@ -893,10 +838,10 @@ inline int pack_scene(const rt_scene_desc &sc, PackedScene &out, bool rebuild_sc
     }
 
     lap = PackLap();
-    const uint32_t n = static_cast<uint32_t>(out.scene.order.size());  // device triangle order = packed BVH order
+    const uint32_t n = with_scene ? static_cast<uint32_t>(out.scene.order.size()) : 0u;  // device triangle order = packed BVH order
     out.attrs.resize(n);
     bool any_tangent = false;
-    if (sc.tri_tangents)
+    if (sc.tri_tangents && with_scene)
         for (size_t i = 0; i < static_cast<size_t>(sc.n_tris) * 3 && !any_tangent; ++i) {
             const float *t = sc.tri_tangents + i * 3;
             any_tangent = !(t[0] == 1.0f && t[1] == 0.0f && t[2] == 0.0f);

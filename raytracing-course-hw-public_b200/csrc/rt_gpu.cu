@@ -31,6 +31,7 @@
 #endif
 #include "text_kernels.cuh"
 #include "repack.h"
+#include "gpu_build.cuh"
 #include "rt_gpu.h"
 
 namespace {
@@ -128,6 +129,14 @@ struct DeviceState {
     DevBuf<uint32_t> texels;
     DevBuf<float> lut;
     DScene scene;
+    // device-side scene build (gpu_build.cuh): H2D copies of the host's arrays, scratch, last result
+    DevBuf<float> in_pos, in_nrm, in_uv, in_tan;
+    DevBuf<uint32_t> in_mat;
+    DevBuf<uint8_t> build_scratch;
+    rtb::Counters *h_counters = nullptr;  // pinned
+    rtb::Arrays built{};                  // device pointers of the last device build (diagnostics)
+    uint32_t built_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n_tris, n_slots, n_wide, root4, stack_need, max_depth, 1 = device build, levels
+    int built_parity = 0;
     // course text scene (rt_gpu_upload_text_scene)
     DevBuf<rt_text_prim> tprims;
     DevBuf<rt_text_light> tlights;
@@ -207,20 +216,199 @@ struct rt_gpu_ctx {
 
 namespace {
 
-int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p) {
+// Scene BVH, triangles and attributes built on the device from the host's arrays (gpu_build.cuh).  Fills d.qnodes4,
+// d.tris, d.attrs (, d.tangents) and the root link / counts in `info`.
+int device_build_scene(DeviceState &d, const rt_scene_desc &sc, double *t_h2d_ms) {
+    using namespace rtb;
+    CU_CHECK(cudaSetDevice(d.device));
+    const uint32_t n = sc.n_tris;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto h2d = [&](auto &buf, const auto *src, size_t count) -> int {
+        if (int rc = buf.alloc(std::max<size_t>(count, 1))) return rc;
+        if (count) CU_CHECK(cudaMemcpyAsync(buf.p, src, count * sizeof(*src), cudaMemcpyHostToDevice, d.stream));
+        return RT_OK;
+    };
+    if (int rc = h2d(d.in_pos, sc.tri_pos, static_cast<size_t>(n) * 9)) return rc;
+    if (int rc = h2d(d.in_nrm, sc.tri_normals, static_cast<size_t>(n) * 9)) return rc;
+    if (int rc = h2d(d.in_uv, sc.tri_uv, static_cast<size_t>(n) * 6)) return rc;
+    if (int rc = h2d(d.in_mat, sc.tri_material, static_cast<size_t>(n))) return rc;
+    if (sc.tri_tangents)
+        if (int rc = h2d(d.in_tan, sc.tri_tangents, static_cast<size_t>(n) * 9)) return rc;
+    if (t_h2d_ms) *t_h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+
+    // scratch carved from one allocation
+    const size_t n_slots = n ? 2 * static_cast<size_t>(n) - 1 : 0;
+    const size_t n_pool = n / kSmall + 2;
+    const size_t n_words = (std::max<size_t>(n_slots, n) + 31) / 32 + 8;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) / 256 * 256;
+        return at;
+    };
+    const size_t o_plo = carve(n * sizeof(float4)), o_phi = carve(n * sizeof(float4));
+    const size_t o_idx0 = carve(n * 4), o_idx1 = carve(n * 4), o_nof0 = carve(n * 4), o_nof1 = carve(n * 4);
+    const size_t o_nodes = carve(std::max<size_t>(n_slots, 1) * sizeof(rt_bvh_node)), o_aux = carve(std::max<size_t>(n_slots, 1) * sizeof(NodeAux));
+    const size_t o_bins0 = carve(n_pool * sizeof(BinSlot)), o_bins1 = carve(n_pool * sizeof(BinSlot));
+    const size_t o_act0 = carve(n_pool * 4), o_act1 = carve(n_pool * 4), o_small = carve((static_cast<size_t>(n) + 1) * 4);
+    const size_t o_words = carve(n_words * 4), o_wscan = carve(n_words * 4);
+    const size_t o_last = carve(static_cast<size_t>(n) + 1), o_mark = carve(n_slots + 1), o_need = carve((n_slots + 1) * 4);
+    const size_t o_fr0 = carve((static_cast<size_t>(n) + 1) * 4), o_fr1 = carve((static_cast<size_t>(n) + 1) * 4), o_fr2 = carve((static_cast<size_t>(n) + 1) * 4);
+    const size_t o_cnt = carve(sizeof(Counters));
+    if (int rc = d.build_scratch.alloc(off)) return rc;
+    uint8_t *base = d.build_scratch.p;
+    if (int rc = d.qnodes4.alloc(std::max<size_t>(n, 1))) return rc;  // a tree over n triangles has fewer than n wide nodes
+    if (int rc = d.tris.alloc(static_cast<size_t>(n) + 1)) return rc;
+    if (int rc = d.attrs.alloc(std::max<size_t>(n, 1))) return rc;
+
+    Arrays A{};
+    A.tri_pos = d.in_pos.p;
+    A.tri_normals = d.in_nrm.p;
+    A.tri_uv = d.in_uv.p;
+    A.tri_tangents = sc.tri_tangents ? d.in_tan.p : nullptr;
+    A.tri_material = d.in_mat.p;
+    A.n = n;
+    A.plo = reinterpret_cast<float4 *>(base + o_plo);
+    A.phi = reinterpret_cast<float4 *>(base + o_phi);
+    A.idx[0] = reinterpret_cast<uint32_t *>(base + o_idx0);
+    A.idx[1] = reinterpret_cast<uint32_t *>(base + o_idx1);
+    A.node_of[0] = reinterpret_cast<uint32_t *>(base + o_nof0);
+    A.node_of[1] = reinterpret_cast<uint32_t *>(base + o_nof1);
+    A.nodes = reinterpret_cast<rt_bvh_node *>(base + o_nodes);
+    A.aux = reinterpret_cast<NodeAux *>(base + o_aux);
+    A.bins[0] = reinterpret_cast<BinSlot *>(base + o_bins0);
+    A.bins[1] = reinterpret_cast<BinSlot *>(base + o_bins1);
+    A.active[0] = reinterpret_cast<uint32_t *>(base + o_act0);
+    A.active[1] = reinterpret_cast<uint32_t *>(base + o_act1);
+    A.small = reinterpret_cast<uint32_t *>(base + o_small);
+    A.words = reinterpret_cast<uint32_t *>(base + o_words);
+    A.wscan = reinterpret_cast<uint32_t *>(base + o_wscan);
+    A.last = base + o_last;
+    A.mark = base + o_mark;
+    A.need = reinterpret_cast<uint32_t *>(base + o_need);
+    A.frontier[0] = reinterpret_cast<uint32_t *>(base + o_fr0);
+    A.frontier[1] = reinterpret_cast<uint32_t *>(base + o_fr1);
+    A.frontier[2] = reinterpret_cast<uint32_t *>(base + o_fr2);
+    A.c = reinterpret_cast<Counters *>(base + o_cnt);
+    A.qnodes4 = d.qnodes4.p;
+    A.tris = d.tris.p;
+    A.attrs = d.attrs.p;
+    A.tangents = nullptr;
+    cudaStream_t st = d.stream;
+    Counters &hc = *d.h_counters;
+    auto fetch_counters = [&]() -> int {
+        CU_CHECK(cudaMemcpyAsync(&hc, A.c, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        return RT_OK;
+    };
+    const bool timing = std::getenv("RT_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    std::string phases;
+    auto lap = [&](const char *name) {  // RT_TIMING only: serialises the build at the phase boundaries
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        std::snprintf(buf, sizeof buf, " %s %.2f", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+        phases += buf;
+        t_last = now;
+    };
+    lap("h2d+alloc");
+    std::memset(d.built_info, 0, sizeof d.built_info);
+    d.built = A;
+    d.built_parity = 0;
+    d.built_info[0] = n;
+    d.built_info[3] = static_cast<uint32_t>(RT_LINK_NONE);
+    d.built_info[6] = 1;
+    kb_init<<<1, 1, 0, st>>>(A);
+    if (n == 0) {  // empty scene: only the null triangle
+        kb_tris<<<1, 256, 0, st>>>(A, 0, 0);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaStreamSynchronize(st));
+        return RT_OK;
+    }
+    const uint32_t g_n = (n + 255) / 256;
+    CU_CHECK(cudaMemsetAsync(A.mark, 0, n_slots + 1, st));
+    kb_setup<<<g_n, 256, 0, st>>>(A);
+    kb_root<<<1, 32, 0, st>>>(A);
+    lap("setup");
+    // big phase.  The host does not know when the last big node is gone: it asks every other level, starting where a
+    // balanced tree over n triangles would first run out of nodes with more than kSmall triangles.
+    int first_check = 0;
+    while ((static_cast<uint64_t>(kSmall) << (first_check + 1)) < n) ++first_check;
+    const uint32_t n_bin_words = (n + 31) / 32;
+    const uint32_t g_split = static_cast<uint32_t>((n_pool + 3) / 4);  // one warp per node
+    int parity = 0;
+    uint32_t level = 0;
+    for (;; ++level) {
+        if (level >= RT_STACK_SIZE) return fail(RT_ERR_CUDA, "device BVH build did not terminate");
+        if (static_cast<int>(level) >= first_check && ((level - first_check) & 1u) == 0) {
+            if (int rc = fetch_counters()) return rc;
+            if (hc.n_active[level & 1] == 0) break;
+        }
+        kb_bin<<<g_n, 256, 0, st>>>(A, level, parity);
+        kb_split<<<g_split, 128, 0, st>>>(A, level);
+        kb_flags<<<g_n, 256, 0, st>>>(A, level, parity);
+        kb_scan<<<1, 1024, 0, st>>>(A.words, A.wscan, n_bin_words, nullptr, &A.c->n_active[level & 1]);
+        kb_scatter<<<g_n, 256, 0, st>>>(A, level, parity);
+        parity ^= 1;
+        if (timing && level < 6) lap(("L" + std::to_string(level)).c_str());
+    }
+    lap("big");
+    CU_CHECK(cudaGetLastError());
+    const bool with_tangents = sc.tri_tangents && hc.any_tangent;
+    if (with_tangents) {
+        if (int rc = d.tangents.alloc(n)) return rc;
+        A.tangents = d.tangents.p;
+    }
+    if (hc.n_small) kb_small<<<(hc.n_small + 3) / 4, 128, 0, st>>>(A, parity);
+    lap("small");
+    kb_tris<<<(n + 1 + 255) / 256, 256, 0, st>>>(A, parity, with_tangents ? 1 : 0);
+    lap("tris");
+    kb_mark_root<<<1, 1, 0, st>>>(A);
+    if (int rc = fetch_counters()) return rc;  // max_depth now covers kb_small's sub-trees
+    for (uint32_t l = 0; l <= hc.max_depth; ++l)  // a wide level consumes at least one binary level
+        kb_mark<<<256, 128, 0, st>>>(A, l);
+    lap("mark");
+    const uint32_t ns32 = static_cast<uint32_t>(n_slots);
+    kb_markwords<<<(ns32 + 255) / 256, 256, 0, st>>>(A, ns32);
+    kb_scan<<<1, 1024, 0, st>>>(A.words, A.wscan, (ns32 + 31) / 32, &A.c->n_wide, nullptr);
+    kb_emit<<<(ns32 + 127) / 128, 128, 0, st>>>(A, ns32);
+    CU_CHECK(cudaGetLastError());
+    if (int rc = fetch_counters()) return rc;
+    lap("emit");
+    if (timing) std::fprintf(stderr, "rt_gpu device build phases (ms, serialised):%s\n", phases.c_str());
+    d.built = A;
+    d.built_parity = parity;
+    d.built_info[1] = ns32;
+    d.built_info[2] = hc.n_wide;
+    d.built_info[3] = hc.n_wide ? 0u : static_cast<uint32_t>(~0);  // root link: wide node 0, or the single leaf at triangle 0
+    d.built_info[4] = hc.stack_need;
+    d.built_info[5] = hc.max_depth;
+    d.built_info[7] = level;
+    if (hc.error) return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_scene: non-finite triangle or a node that cannot be quantised");
+    if (hc.stack_need > RT_EXT_STACK_CAP) return fail(RT_ERR_BAD_SCENE, "rt_gpu_upload_scene: the 4-wide tree needs more than RT_EXT_STACK_CAP traversal-stack entries");
+    return RT_OK;
+}
+
+int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedScene &p, bool device_built) {
     CU_CHECK(cudaSetDevice(d.device));
 #if RT_EXT_WIDE8  // only the node format the traversal kernel was built for goes to the device
     if (int rc = d.qnodes8.upload(p.scene.qnodes8, d.stream)) return rc;
     if (int rc = d.lqnodes8.upload(p.light.qnodes8, d.stream)) return rc;
 #else
-    if (int rc = d.qnodes4.upload(p.scene.qnodes4, d.stream)) return rc;
+    if (!device_built)
+        if (int rc = d.qnodes4.upload(p.scene.qnodes4, d.stream)) return rc;
     if (int rc = d.lqnodes4.upload(p.light.qnodes4, d.stream)) return rc;
 #endif
-    if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
+    if (!device_built) {
+        if (int rc = d.tris.upload(p.scene.tris, d.stream)) return rc;
+        if (int rc = d.attrs.upload(p.attrs, d.stream)) return rc;
+        if (int rc = d.tangents.upload(p.tangents, d.stream)) return rc;
+        std::memset(d.built_info, 0, sizeof d.built_info);
+    }
     if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
     if (int rc = d.lsample.upload(p.light_sample, d.stream)) return rc;
-    if (int rc = d.attrs.upload(p.attrs, d.stream)) return rc;
-    if (int rc = d.tangents.upload(p.tangents, d.stream)) return rc;
     if (int rc = d.light_extra.upload(p.light_extra, d.stream)) return rc;
     if (int rc = d.materials.upload(p.materials, d.stream)) return rc;
     if (int rc = d.textures.upload(p.textures, d.stream)) return rc;
@@ -241,6 +429,11 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     d.scene.light_sample = d.lsample.p;
     d.scene.attrs = d.attrs.p;
     d.scene.tangents = p.tangents.empty() ? nullptr : d.tangents.p;
+    if (device_built) {
+        d.scene.scene.root4 = static_cast<int32_t>(d.built_info[3]);
+        d.scene.scene.n_tris = d.built_info[0] + 1;
+        d.scene.tangents = d.built.tangents;
+    }
     d.scene.light_extra = d.light_extra.p;
     d.scene.materials = d.materials.p;
     d.scene.textures = d.textures.p;
@@ -485,6 +678,7 @@ int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
         CU_CHECK(cudaEventCreate(&d->ev_red1));
         CU_CHECK(cudaMallocHost(reinterpret_cast<void **>(&d->h_stats), 4 * sizeof(unsigned long long)));
         std::memset(d->h_stats, 0, 4 * sizeof(unsigned long long));
+        CU_CHECK(cudaMallocHost(reinterpret_cast<void **>(&d->h_counters), sizeof(rtb::Counters)));
         int occ_e = 0, occ_s = 0;
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, RT_K_EXTEND, rt::kExtendThreads, 0));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, rt::k_shade, rt::kShadeThreads, 0));
@@ -546,6 +740,8 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         if (d.h_stats) cudaFreeHost(d.h_stats);
         if (d.h_means) cudaFreeHost(d.h_means);
         if (d.h_stage) cudaFreeHost(d.h_stage);
+        if (d.h_counters) cudaFreeHost(d.h_counters);
+        d.in_pos.release(); d.in_nrm.release(); d.in_uv.release(); d.in_tan.release(); d.in_mat.release(); d.build_scratch.release();
         d.counters.release(); d.stats.release();
         d.prim_ids.release(); d.rgb8.release();
         for (cudaEvent_t e : d.event_pool) cudaEventDestroy(e);
@@ -605,12 +801,27 @@ int rt_gpu_upload_scene(rt_gpu_ctx *ctx, const rt_scene_desc *scene) {
     struct ResetTimes {
         ~ResetTimes() { rt::pack_times() = nullptr; }
     } reset_times;
-    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : rt::RT_PACK_Q4)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects, depth > 64, non-finite box, or a 4-wide tree whose traversal needs more than RT_EXT_STACK_CAP stack entries)");
+    // Default: the scene BVH, triangles and attributes are built on the device (gpu_build.cuh); the host packs only the
+    // light BVH, the materials and the textures.  The host builder (sah_build.h) remains for RT_SCENE_KEEP_HOST_BVH, for
+    // the 8-wide build and as the A/B reference (RT_HOST_BUILD=1).
+    const char *host_env = std::getenv("RT_HOST_BUILD");
+    const bool device_build = !keep && !RT_EXT_WIDE8 && !(host_env && std::atoi(host_env) != 0);
+    if (int rc = rt::pack_scene(*scene, packed, !keep, RT_EXT_WIDE8 ? rt::RT_PACK_Q8 : rt::RT_PACK_Q4, !device_build)) return fail(rc, "rt_gpu_upload_scene: scene cannot be re-packed (inner node with objects, depth > 64, non-finite box, or a 4-wide tree whose traversal needs more than RT_EXT_STACK_CAP stack entries)");
     const auto t_pack1 = std::chrono::steady_clock::now();
-    for (auto &d : ctx->devs)
-        if (int rc = upload_to_device(*d, *scene, packed)) return rc;
+    double t_h2d = 0.0, t_build = 0.0;
+    for (auto &d : ctx->devs) {
+        if (device_build) {
+            const auto tb0 = std::chrono::steady_clock::now();
+            if (int rc = device_build_scene(*d, *scene, &t_h2d)) return rc;
+            t_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
+        }
+        if (int rc = upload_to_device(*d, *scene, packed, device_build)) return rc;
+    }
     if (std::getenv("RT_TIMING")) {
         const auto t_up = std::chrono::steady_clock::now();
+        if (device_build)
+            std::fprintf(stderr, "rt_gpu_upload_scene: device build %.2f ms (of which H2D of the host arrays %.2f ms): %u levels, depth %u, %u wide nodes, stack need %u\n",
+                         t_build, t_h2d, ctx->devs[0]->built_info[7], ctx->devs[0]->built_info[5], ctx->devs[0]->built_info[2], ctx->devs[0]->built_info[4]);
         std::fprintf(stderr,
                      "rt_gpu_upload_scene: re-pack %.1f ms (SAH build %.1f, triangles + binary nodes %.1f, collapse %.1f, quantise %.1f, "
                      "attributes %.1f, materials/texels %.1f; the light BVHs are inside the middle three), H2D %.1f ms\n",
@@ -860,6 +1071,32 @@ int rt_gpu_fp32_peak(rt_gpu_ctx *ctx, double *tflops) {
         if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
     *tflops = best;
+    return RT_OK;
+}
+
+int rt_gpu_debug_get_bvh(rt_gpu_ctx *ctx, int which, void *dst, size_t *bytes) {
+    if (!ctx || !bytes) return fail(RT_ERR_INVALID_ARG, "rt_gpu_debug_get_bvh: null argument");
+    if (!ctx->have_scene || ctx->text_scene) return fail(RT_ERR_NO_SCENE, "rt_gpu_debug_get_bvh: no triangle scene uploaded");
+    DeviceState &d = *ctx->devs[0];
+    CU_CHECK(cudaSetDevice(d.device));
+    const uint32_t n = d.built_info[0], n_slots = d.built_info[1], n_wide = d.built_info[2];
+    const bool dev = d.built_info[6] != 0;
+    const void *src = nullptr;
+    size_t sz = 0;
+    switch (which) {
+    case 0: src = d.built_info; sz = sizeof d.built_info; break;
+    case 1: if (dev) { src = d.built.nodes; sz = static_cast<size_t>(n_slots) * sizeof(rt_bvh_node); } break;
+    case 2: if (dev) { src = d.built.idx[d.built_parity]; sz = static_cast<size_t>(n) * 4; } break;
+    case 3: if (dev) { src = d.qnodes4.p; sz = static_cast<size_t>(n_wide) * sizeof(QNode4); } break;
+    case 4: if (dev) { src = d.tris.p; sz = (static_cast<size_t>(n) + 1) * sizeof(DTri); } break;
+    default: return fail(RT_ERR_INVALID_ARG, "rt_gpu_debug_get_bvh: unknown selector");
+    }
+    if (dst) {
+        if (*bytes < sz) return fail(RT_ERR_INVALID_ARG, "rt_gpu_debug_get_bvh: buffer too small");
+        if (which == 0) std::memcpy(dst, src, sz);
+        else if (sz) CU_CHECK(cudaMemcpy(dst, src, sz, cudaMemcpyDeviceToHost));
+    }
+    *bytes = sz;
     return RT_OK;
 }
 

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("RT_GPU_LIB") or os.path.join(_abi.PKG_DIR, "librt_gpu
 
 # every symbol include/rt_gpu.h declares
 SYMBOLS = ["rt_gpu_create", "rt_gpu_destroy", "rt_gpu_upload_scene", "rt_gpu_upload_text_scene", "rt_gpu_render", "rt_gpu_readback",
-           "rt_gpu_accum_device_ptr", "rt_gpu_readback_rgb8", "rt_gpu_set_profiling", "rt_gpu_fp32_peak", "rt_gpu_last_error",
+           "rt_gpu_accum_device_ptr", "rt_gpu_readback_rgb8", "rt_gpu_set_profiling", "rt_gpu_debug_get_bvh", "rt_gpu_fp32_peak", "rt_gpu_last_error",
            "rt_gpu_device_count", "rt_gpu_abi_version"]
 
 _lib = None
@@ -33,6 +33,7 @@ def lib():
         L.rt_gpu_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.rt_gpu_readback_rgb8.argtypes = [C.c_void_p, C.c_void_p]
         L.rt_gpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.rt_gpu_debug_get_bvh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]
         L.rt_gpu_fp32_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.rt_gpu_last_error.restype = C.c_char_p
         _lib = L
@@ -131,6 +132,15 @@ class RtGpu:
         ids = np.empty((height, width), np.int32)
         _check(lib().rt_gpu_readback(self._h, None, ids.ctypes.data_as(C.c_void_p), None), "rt_gpu_readback")
         return ids
+
+    def debug_bvh(self, which, dtype):
+        """Diagnostic download of the device-built scene BVH (rt_gpu_debug_get_bvh); numpy array of `dtype`."""
+        n = C.c_size_t(0)
+        _check(lib().rt_gpu_debug_get_bvh(self._h, which, None, C.byref(n)), "rt_gpu_debug_get_bvh")
+        out = np.zeros(n.value // np.dtype(dtype).itemsize, dtype)
+        if n.value:
+            _check(lib().rt_gpu_debug_get_bvh(self._h, which, out.ctypes.data_as(C.c_void_p), C.byref(n)), "rt_gpu_debug_get_bvh")
+        return out
 
     def fp32_peak_tflops(self):
         v = C.c_double()

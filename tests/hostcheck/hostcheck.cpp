@@ -235,55 +235,116 @@ int hc_wide8_stats(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *ids
 
 // Build statistics of the library's SAH builder: out[0] = seconds, out[1] = inner nodes, out[2] = leaves,
 // out[3] = max leaf size, out[4] = max depth, out[5] = 1 when every triangle id appears exactly once.
-int hc_sah_stats(const rt_scene_desc *sc, double *out) {
-    BuiltBvh b;
-    const auto t0 = std::chrono::steady_clock::now();
-    build_sah_bvh(sc->tri_pos, sc->scene_bvh.objects, sc->scene_bvh.n_objects, b);
-    out[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    double inner = 0, leaves = 0, max_leaf = 0;
-    std::vector<int> depth(b.nodes.size(), -1);
+// Invariants and SAH cost of a binary tree in the reference's node format over the scene's triangles (any builder:
+// sah_build.h on the host, gpu_build.cuh downloaded from the device).  out[1] inner nodes, [2] leaves, [3] largest leaf,
+// [4] depth, [5] 1 when every triangle sits in exactly one leaf, every leaf box is EXACTLY the union of its triangles and
+// every inner box is exactly the union of its children, [6] SAH cost = (sum of inner areas + sum of leaf area x
+// triangles) / root area, [7] 1 when the slots follow sah_build.h's layout (left = i + 1, right = i + 2 * n_left)
+static int tree_stats(const rt_scene_desc *sc, const rt_bvh_node *nodes, size_t n_nodes, const uint32_t *objects, size_t n_objects,
+                      uint32_t root, double *out) {
+    double inner = 0, leaves = 0, max_leaf = 0, cost = 0;
+    std::vector<int> depth(n_nodes, -1);
     std::vector<uint32_t> todo;
     int max_depth = 0;
     std::vector<uint8_t> seen(sc->n_tris, 0);
-    bool once = true;
-    if (b.root != RT_NO_CHILD && !b.objects.empty()) {
-        todo.push_back(b.root);
-        depth[b.root] = 0;
+    bool once = true, layout = true;
+    auto area = [](const rt_bvh_node &n) {
+        const double dx = (double)n.bmax[0] - n.bmin[0], dy = (double)n.bmax[1] - n.bmin[1], dz = (double)n.bmax[2] - n.bmin[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    std::vector<uint32_t> count(n_nodes, 0);
+    std::vector<uint32_t> order;
+    if (root != RT_NO_CHILD && n_objects) {
+        todo.push_back(root);
+        depth[root] = 0;
     }
     while (!todo.empty()) {
         const uint32_t i = todo.back();
         todo.pop_back();
-        const rt_bvh_node &nd = b.nodes[i];
+        order.push_back(i);
+        const rt_bvh_node &nd = nodes[i];
         max_depth = std::max(max_depth, depth[i]);
         if (nd.left_child == RT_NO_CHILD && nd.right_child == RT_NO_CHILD) {
             ++leaves;
+            if (nd.obj_end <= nd.obj_begin || nd.obj_end > n_objects) return -2;
             max_leaf = std::max(max_leaf, (double)(nd.obj_end - nd.obj_begin));
+            count[i] = nd.obj_end - nd.obj_begin;
+            cost += area(nd) * count[i];
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
             for (uint32_t k = nd.obj_begin; k < nd.obj_end; ++k) {
-                const uint32_t id = b.objects[k];
-                if (id >= sc->n_tris || seen[id]) once = false;
-                else seen[id] = 1;
-                // the leaf box must contain the triangle
+                const uint32_t id = objects[k];
+                if (id >= sc->n_tris || seen[id]) { once = false; continue; }
+                seen[id] = 1;
                 for (int v = 0; v < 3; ++v)
                     for (int a = 0; a < 3; ++a) {
                         const float x = sc->tri_pos[(size_t)id * 9 + v * 3 + a];
-                        if (x < nd.bmin[a] || x > nd.bmax[a]) once = false;
+                        lo[a] = std::min(lo[a], x);
+                        hi[a] = std::max(hi[a], x);
                     }
             }
+            for (int a = 0; a < 3; ++a)
+                if (lo[a] != nd.bmin[a] || hi[a] != nd.bmax[a]) once = false;  // the leaf box is the union of its triangles
         } else {
             ++inner;
+            cost += area(nd);
+            if (nd.left_child != i + 1) layout = false;
             for (uint32_t c : {nd.left_child, nd.right_child}) {
-                if (c == RT_NO_CHILD || c >= b.nodes.size()) return -1;
-                const rt_bvh_node &ch = b.nodes[c];
-                for (int a = 0; a < 3; ++a)
-                    if (ch.bmin[a] < nd.bmin[a] || ch.bmax[a] > nd.bmax[a]) once = false;  // child box inside parent box
+                if (c == RT_NO_CHILD || c >= n_nodes) return -1;
                 depth[c] = depth[i] + 1;
                 todo.push_back(c);
             }
+            const rt_bvh_node &l = nodes[nd.left_child], &r = nodes[nd.right_child];
+            for (int a = 0; a < 3; ++a)
+                if (std::min(l.bmin[a], r.bmin[a]) != nd.bmin[a] || std::max(l.bmax[a], r.bmax[a]) != nd.bmax[a]) once = false;
         }
     }
-    for (uint32_t k = 0; k < sc->scene_bvh.n_objects; ++k)
-        if (!seen[sc->scene_bvh.objects[k]]) once = false;
+    for (size_t k = order.size(); k-- > 0;) {  // children were pushed after their parent: reverse order sums the counts
+        const rt_bvh_node &nd = nodes[order[k]];
+        if (nd.left_child != RT_NO_CHILD) {
+            count[order[k]] = count[nd.left_child] + count[nd.right_child];
+            if (nd.right_child != order[k] + 2 * count[nd.left_child]) layout = false;
+        }
+    }
+    for (uint32_t id = 0; id < sc->n_tris; ++id)
+        if (!seen[id] && n_objects == sc->n_tris) once = false;
     out[1] = inner; out[2] = leaves; out[3] = max_leaf; out[4] = max_depth; out[5] = once ? 1.0 : 0.0;
+    out[6] = root != RT_NO_CHILD && n_objects ? cost / area(nodes[root]) : 0.0;
+    out[7] = layout ? 1.0 : 0.0;
+    return 0;
+}
+
+int hc_sah_stats(const rt_scene_desc *sc, double *out) {
+    BuiltBvh b;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (sc->scene_bvh.n_objects) build_sah_bvh(sc->tri_pos, sc->scene_bvh.objects, sc->scene_bvh.n_objects, b);
+    else build_sah_bvh(sc->tri_pos, nullptr, sc->n_tris, b);
+    out[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return tree_stats(sc, b.nodes.data(), b.nodes.size(), b.objects.data(), b.objects.size(), b.root, out);
+}
+
+// the same for a tree given as arrays (the device-built tree, downloaded through rt_gpu_debug_get_bvh)
+int hc_tree_stats(const rt_scene_desc *sc, const rt_bvh_node *nodes, uint64_t n_nodes, const uint32_t *objects, uint64_t n_objects, double *out) {
+    out[0] = 0.0;
+    return tree_stats(sc, nodes, n_nodes, objects, n_objects, n_objects ? 0u : RT_NO_CHILD, out);
+}
+
+// containment invariant (walk4) of a 4-wide tree given as arrays; out as hc_wide_containment
+int hc_wide_containment_arrays(const QNode4 *qnodes4, uint64_t n_nodes, int32_t root4, const DTri *tris, uint64_t n_tris_with_null, double *out) {
+    PackedBvh b;
+    b.qnodes4.assign(qnodes4, qnodes4 + n_nodes);
+    b.tris.assign(tris, tris + n_tris_with_null);
+    b.root4 = root4;
+    uint64_t bad = 0, checked = 0, n_tris = 0;
+    if (root4 != RT_LINK_NONE) {
+        for (const QNode4 &q : b.qnodes4)
+            for (int c = 0; c < 4; ++c)
+                if (q.link[c] >= 0 ? (uint64_t)q.link[c] >= n_nodes : (uint64_t)(uint32_t)~q.link[c] >= n_tris_with_null) return -1;
+        walk4(b, root4, bad, checked, n_tris, ~static_cast<int32_t>(b.tris.size() - 1));
+    }
+    out[0] = (double)checked;
+    out[1] = (double)bad;
+    out[2] = (double)n_tris;
+    out[3] = (double)detail::stack_need4(b.qnodes4, root4, ~static_cast<int32_t>(b.tris.size() - 1));
     return 0;
 }
 

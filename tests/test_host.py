@@ -219,11 +219,11 @@ def test_sah_rebuilt_tree_gives_reference_ids(name, hc, manifest, golden_scene):
 
 def test_sah_builder_invariants_on_the_260k_scene(hc, big_scene):
     d = big_scene.desc()
-    out = (C.c_double * 6)()
+    out = (C.c_double * 8)()
     assert hc.hc_sah_stats(C.byref(d), out) == 0
-    secs, inner, leaves, max_leaf, max_depth, ok = list(out)
-    print(f"sah build: {secs * 1e3:.0f} ms, {inner:.0f} inner, {leaves:.0f} leaves, max leaf {max_leaf:.0f}, depth {max_depth:.0f}")
-    assert ok == 1.0  # every triangle exactly once, boxes nested
+    secs, inner, leaves, max_leaf, max_depth, ok, cost, layout = list(out)
+    print(f"sah build: {secs * 1e3:.0f} ms, {inner:.0f} inner, {leaves:.0f} leaves, max leaf {max_leaf:.0f}, depth {max_depth:.0f}, SAH cost {cost:.2f}")
+    assert ok == 1.0 and layout == 1.0  # every triangle exactly once, every box the exact union of what is below it
     assert inner == leaves - 1 and max_leaf <= 8 and max_depth < 62
     hc.hc_set_rebuild(1)
     try:
