@@ -276,6 +276,36 @@ def test_cli_drop_in_matches_reference_binary(scene_dir, tmp_path):
             assert mae < 1.0, (name, mae)  # tiny scene: 0.52 LSB reference-vs-reference at 4096 spp
 
 
+def test_cli_drop_in_accepts_course_text_scenes(tmp_path):
+    """The reference CLI surface covers both inputs (north star: "the same course scene-*.txt and glTF inputs"): the C++
+    drop-in dispatches *.txt to rt_text_scene_parse + rt_gpu_upload_text_scene like the Python CLI does; 0 for width /
+    height / samples takes the file's DIMENSIONS / SAMPLES.  Same library, same seed -> the same PPM bytes."""
+    import subprocess
+    from conftest import ROOT
+    from rt_b200 import cli
+
+    exe = os.path.join(ROOT, "bin", "raytracer_b200")
+    if not os.path.exists(exe):
+        pytest.skip("bin/raytracer_b200 not built (reference headers absent at build time)")
+    txt = tmp_path / "scene.txt"
+    txt.write_text("DIMENSIONS 96 64\nRAY_DEPTH 4\nSAMPLES 32\nBG_COLOR 0.2 0.3 0.5\n"
+                   "CAMERA_POSITION 0 1 4\nCAMERA_RIGHT 1 0 0\nCAMERA_UP 0 1 0\nCAMERA_FORWARD 0 0 -1\nCAMERA_FOV_X 1.2\n"
+                   "NEW_PRIMITIVE\nPLANE 0 1 0\nCOLOR 0.8 0.8 0.8\n"
+                   "NEW_PRIMITIVE\nELLIPSOID 0.7 0.9 0.7\nPOSITION -1 0.9 0\nCOLOR 0.9 0.3 0.2\nMETALLIC\n"
+                   "NEW_PRIMITIVE\nBOX 0.5 0.5 0.5\nPOSITION 1 0.5 0\nROTATION 0 0.3826834 0 0.9238795\nCOLOR 0.2 0.7 0.3\nDIELECTRIC\nIOR 1.4\n"
+                   "NEW_PRIMITIVE\nTRIANGLE -1 3 -1 1 3 -1 0 3 1\nEMISSION 12 12 12\n")
+    for dims in (("0", "0", "0"), ("48", "40", "8")):
+        subprocess.run([exe, str(txt), *dims, str(tmp_path / "cxx.ppm")], check=True)
+        assert cli.main(["prog", str(txt), *dims, str(tmp_path / "py.ppm")]) == 0
+        a, b = _read_ppm(tmp_path / "cxx.ppm"), _read_ppm(tmp_path / "py.ppm")
+        assert a.shape == b.shape == ((64, 96, 3) if dims[0] == "0" else (40, 48, 3))
+        assert np.array_equal(a, b) and a.std() > 5  # identical, and not a constant image
+    bad = tmp_path / "bad.txt"
+    bad.write_text("DIMENSIONS 4 4\nNEW_PRIMITIVE\nTORUS 1 2\n")
+    r = subprocess.run([exe, str(bad), "0", "0", "0", str(tmp_path / "x.ppm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot parse text scene" in r.stderr
+
+
 def test_eight_wide_build_keeps_parity():
     """The optional 8-wide traversal build (k_extend8, -DRT_EXT_WIDE8=1) passes the same id / path-by-path / statistical
     parity tests; it is loaded through RT_GPU_LIB in a fresh interpreter."""
