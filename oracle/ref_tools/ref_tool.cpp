@@ -42,6 +42,8 @@ static Scene load(const char *path, unsigned w, unsigned h, unsigned spp) {
     // main.cpp:29-31 loads ENV_MAP_PATH when the compile-time USE_ENV_MAP is set; the harness takes the path from the
     // environment instead so that Scene::bg_at (scene.h:83-89) can be exercised without touching config.h
     if (const char *env = std::getenv("RT_ENV_MAP")) scene.bg = geometry::Texture::load_img(env);
+    // likewise the compile-time ADD_LIGHT_TRIANGLE (config.h:39-47; scene.h:479-498 appends the object inside the loader)
+    if (const char *lt = std::getenv("RT_ADD_LIGHT_TRIANGLE"); lt && std::atoi(lt)) rt_flatten::append_light_triangle(scene);
     scene.camera.width = w;
     scene.camera.height = h;
     scene.samples = spp;

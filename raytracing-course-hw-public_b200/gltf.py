@@ -130,7 +130,12 @@ def _load_texture(path):
 _COMPONENT = {5121: np.uint8, 5123: np.uint16, 5125: np.uint32}
 
 
-def load_gltf(path, aspect_ratio, build_bvh=True, env_map=None):
+# config.h:39-47: the extra light source, in camera coordinates (right, up, forward)
+LIGHT_TRIANGLE_INTENSITY = 10.0
+LIGHT_TRIANGLE_RELATIVE_POS = ((10.0, 0.0, -0.1), (0.0, 10.0, -0.1), (0.0, -10.0, -0.1))
+
+
+def load_gltf(path, aspect_ratio, build_bvh=True, env_map=None, add_light_triangle=None):
     """parse_gltf_scene(path, ar) + RaytracerStaticContext (both BVH builds) -> SceneData.
 
     `aspect_ratio` is width/height as the CLI passes it (src/main.cpp:27).  `env_map`: image file used as the
@@ -306,6 +311,32 @@ def load_gltf(path, aspect_ratio, build_bvh=True, env_map=None):
         s.tri_material = np.concatenate(mat_chunks)
     else:
         s.tri_tangents = np.zeros((0, 3, 3), F)
+    if add_light_triangle is None:
+        add_light_triangle = os.environ.get("RT_ADD_LIGHT_TRIANGLE", "0") not in ("", "0")
+    if add_light_triangle:
+        # ADD_LIGHT_TRIANGLE (config.h:39-47, false at HEAD; scene.h:479-498): one more object after all others — the
+        # triangle w + (x * right + y * up + z * forward), default material (geometry.h:604-609) with emission 10,
+        # its own normal on every vertex, uv 0, tangent (1, 0, 0)
+        x, y, z, w = s.camera_right.astype(F), s.camera_up.astype(F), s.camera_forward.astype(F), s.camera_position.astype(F)
+        tri = np.stack([w + ((F(r[0]) * x + F(r[1]) * y) + F(r[2]) * z) for r in LIGHT_TRIANGLE_RELATIVE_POS]).astype(F)
+        v, u = tri[1] - tri[0], tri[2] - tri[0]
+        c = np.array([[v[1] * u[2] - v[2] * u[1], v[2] * u[0] - v[0] * u[2], v[0] * u[1] - v[1] * u[0]]], F)
+        rec = np.zeros((), MATERIAL_DTYPE)
+        rec["color"] = (1, 1, 1, 1)
+        rec["emission"] = (LIGHT_TRIANGLE_INTENSITY,) * 3
+        rec["roughness"], rec["metallic"], rec["ior"] = 1.0, 1.0, 1.5
+        rec["color_tex"] = rec["emissive_tex"] = rec["metallic_roughness_tex"] = rec["normal_tex"] = -1
+        key = rec.tobytes()
+        if key not in mat_index:
+            mat_index[key] = len(materials)
+            materials.append(rec)
+        empty = s.n_tris == 0
+        cat = (lambda a, b: b) if empty else (lambda a, b: np.concatenate([a, b]))
+        s.tri_pos = cat(s.tri_pos, tri[None])
+        s.tri_normals = cat(s.tri_normals, np.repeat(_normalize(c)[:, None, :], 3, axis=1).astype(F))
+        s.tri_uv = cat(s.tri_uv, np.zeros((1, 3, 2), F))
+        s.tri_tangents = cat(s.tri_tangents, np.tile(np.array([1, 0, 0], F), (1, 3, 1)))
+        s.tri_material = cat(s.tri_material, np.array([mat_index[key]], np.uint32))
     s.materials = np.array(materials, MATERIAL_DTYPE) if materials else np.zeros(0, MATERIAL_DTYPE)
     if env_map is not None:
         env = _load_texture(env_map)

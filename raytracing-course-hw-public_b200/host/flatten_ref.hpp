@@ -175,6 +175,25 @@ inline void flatten(const Scene &scene, const RaytracerStaticContext &ctx, FlatS
     flatten(scene, &ctx.scene_bvh, ctx.light_bvh, out);
 }
 
+// Run-time form of the reference's compile-time ADD_LIGHT_TRIANGLE (config.h:39-47, false at HEAD): what
+// parse_gltf_scene appends under that switch (scene.h:479-498) — one emissive triangle given in camera coordinates
+// (LIGHT_TRIANGLE_RELATIVE_POS: 0.1 behind the camera plane), intensity LIGHT_TRIANGLE_INTENSITY, default material.
+// A reference built with ADD_LIGHT_TRIANGLE = true needs nothing from this: its loader has appended the object already.
+inline void append_light_triangle(Scene &scene) {
+    geometry::Object light;
+    const geometry::vec3 axes[3] = {scene.camera.right, scene.camera.up, scene.camera.forward};
+    geometry::vec3 *corner[3] = {&light.shape.a(), &light.shape.b(), &light.shape.c()};
+    for (int v = 0; v < 3; ++v) {
+        const auto &rel = LIGHT_TRIANGLE_RELATIVE_POS[v];
+        *corner[v] = scene.camera.position + geometry::transform3(geometry::vec3(rel[0], rel[1], rel[2]), axes[0], axes[1], axes[2]);
+    }
+    light.material.emission = {LIGHT_TRIANGLE_INTENSITY, LIGHT_TRIANGLE_INTENSITY, LIGHT_TRIANGLE_INTENSITY};
+    light.attrs.normals.fill(light.shape.normal());
+    light.attrs.tex_coords.fill(geometry::vec2(0, 0));
+    light.attrs.tangents.fill(geometry::vec3(1, 0, 0));
+    scene.objects.push_back(light);
+}
+
 // raytracer.h:444-447 alone: the light BVH, whose object order the light sampler indexes.
 inline BVH build_light_bvh(const Scene &scene) {
     return BVH::build(std::span(scene.objects),

@@ -16,6 +16,7 @@
 //   RT_GPUS   number of GPUs of this box to split the samples over (default 1)
 //   RT_SEED   Philox seed (default 0)
 //   RT_HOST_SCENE_BVH  1: also build the reference's scene BVH and pass it (default: the library builds its own)
+//   RT_ADD_LIGHT_TRIANGLE  1: the extra light source of the reference's compile-time ADD_LIGHT_TRIANGLE (config.h:39-47)
 //   RT_ENV_MAP  image file used as the equirectangular environment map Scene::bg (the run-time form of the
 //             reference's compile-time USE_ENV_MAP / ENV_MAP_PATH, src/config.h:35-37)
 #define STB_IMAGE_IMPLEMENTATION
@@ -111,6 +112,7 @@ int main(int argc, char **argv) try {
     scene.bg_color = {ENV_MAP_INTENSITY, ENV_MAP_INTENSITY, ENV_MAP_INTENSITY};
     if constexpr (USE_ENV_MAP) scene.bg = geometry::Texture::load_img(ENV_MAP_PATH);  // main.cpp:29-31
     if (const char *env = std::getenv("RT_ENV_MAP")) scene.bg = geometry::Texture::load_img(env);
+    if (env_uint("RT_ADD_LIGHT_TRIANGLE", 0)) rt_flatten::append_light_triangle(scene);  // config.h:39-47 at run time
     scene.camera.width = width;
     scene.camera.height = height;
     scene.samples = samples;

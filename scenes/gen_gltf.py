@@ -13,6 +13,7 @@ Scenes
   small_lights same + 32 emissive triangles
   big          "Sponza-scale" corridor, 260 160 triangles, env lit
   big_lights   same + 32 emissive triangles = 260 192
+  texmaps      texall with every roughness >= 0.35 (well-conditioned: held to the tight path-by-path bound)
   texall       every loader / material feature: node hierarchy (matrix + TRS, non-uniform
                scale), u8/u16/u32 indices, triangle strip, missing normals, base-colour
                texture with alpha (PNG), normal map, metallic-roughness map, emissive map,
@@ -313,30 +314,35 @@ def tiny():
     return g
 
 
-def texall():
+def texall(name="texall", rough_floor=0.0):
+    """`texmaps` is the same scene with every roughness at least `rough_floor` = 0.35: texall's alpha = 0.0016
+    near-mirrors make the reference's own GGX D term ill-conditioned in float32 (1e-2 relative noise between any two
+    operation orders), which forces a loose per-pixel bound on the path-by-path test; texmaps keeps all four texture
+    maps, the alpha coverage, the node hierarchy and the index types, and is held to the tight bound."""
     rng = np.random.default_rng(7)
-    g = GltfBuilder("texall")
+    g = GltfBuilder(name)
+    rf = lambda r: float(max(r, rough_floor))
     size = 64
     base = checker_texture(rng, size, 8)
     alpha = np.full((size, size, 1), 255, np.uint8)
     yy, xx = np.mgrid[0:size, 0:size]
     alpha[((xx // 8 + yy // 8) % 3 == 0)] = 90
-    t_base = g.texture("texall_base.png", png_bytes(np.concatenate([base, alpha], -1)))
+    t_base = g.texture(name + "_base.png", png_bytes(np.concatenate([base, alpha], -1)))
     # normal map: gentle waves
     nx = 0.35 * np.sin(xx * 2 * np.pi / 16.0)
     ny = 0.35 * np.cos(yy * 2 * np.pi / 12.0)
     nzc = np.sqrt(np.maximum(0.0, 1 - nx * nx - ny * ny))
     nm = np.clip((np.stack([nx, ny, nzc], -1) * 0.5 + 0.5) * 255, 0, 255).astype(np.uint8)
-    t_norm = g.texture("texall_normal.png", png_bytes(nm))
+    t_norm = g.texture(name + "_normal.png", png_bytes(nm))
     # metallic (B) roughness (G)
     mr = np.zeros((size, size, 3), np.uint8)
-    mr[..., 1] = np.clip(40 + 3 * xx, 0, 255)
+    mr[..., 1] = np.clip(np.maximum(40 + 3 * xx, int(np.ceil(rough_floor * 255))), 0, 255)
     mr[..., 2] = np.where(yy < size // 2, 255, 30)
-    t_mr = g.texture("texall_mr.ppm", ppm_bytes(mr))
+    t_mr = g.texture(name + "_mr.ppm", ppm_bytes(mr))
     em = np.zeros((size, size, 3), np.uint8)
     em[16:48, 16:48] = [255, 180, 90]
-    t_em = g.texture("texall_emissive.ppm", ppm_bytes(em))
-    t_one = g.texture("texall_1x1.ppm", ppm_bytes(np.array([[[200, 120, 60]]], np.uint8)))
+    t_em = g.texture(name + "_emissive.ppm", ppm_bytes(em))
+    t_one = g.texture(name + "_1x1.ppm", ppm_bytes(np.array([[[200, 120, 60]]], np.uint8)))
     g.extensions_used.add("KHR_materials_emissive_strength")
 
     m_ground = g.material(pbrMetallicRoughness={"baseColorTexture": {"index": t_base},
@@ -347,11 +353,11 @@ def texall():
                         emissiveFactor=[1.0, 1.0, 1.0], emissiveTexture={"index": t_em},
                         extensions={"KHR_materials_emissive_strength": {"emissiveStrength": 4.0}})
     m_alpha = g.material(pbrMetallicRoughness={"baseColorFactor": [0.3, 0.6, 0.9, 0.5], "metallicFactor": 0.2,
-                                               "roughnessFactor": 0.1})
+                                               "roughnessFactor": rf(0.1)})
     m_one = g.material(pbrMetallicRoughness={"baseColorTexture": {"index": t_one}, "metallicFactor": 0.0,
-                                             "roughnessFactor": 0.02})
+                                             "roughnessFactor": rf(0.02)})
     m_mirror = g.material(pbrMetallicRoughness={"baseColorFactor": [0.9, 0.9, 0.95, 1.0], "metallicFactor": 1.0,
-                                                "roughnessFactor": 0.0})
+                                                "roughnessFactor": rf(0.0)})
 
     # ground: 8x8 grid, textured, with normals
     P, N, UV, T = grid(8, 8, lambda u, v: np.stack([(u - 0.5) * 8, 0.05 * np.sin(6 * u) * np.cos(5 * v), (v - 0.5) * 8], -1))
@@ -387,6 +393,7 @@ def texall():
 SCENES = {
     "tiny": tiny,
     "texall": texall,
+    "texmaps": lambda: texall("texmaps", 0.35),
     "small": lambda: corridor("small", 0.1, False),
     "small_lights": lambda: corridor("small_lights", 0.1, True),
     "medium_lights": lambda: corridor("medium_lights", 0.3, True),

@@ -74,7 +74,9 @@ def big_scene(scene_dir):
     reference's flattening; test_host.py checks that on the small scenes and, when oracle/_ref exists, on this one)."""
     from rt_b200 import gltf
 
-    return gltf.load_gltf(scene_dir("big_lights"), 1.0)
+    sc = gltf.load_gltf(scene_dir("big_lights"), 1.0)
+    sc.source_path = scene_dir("big_lights")
+    return sc
 
 
 def rel_mse(a, b):

@@ -19,6 +19,9 @@ from rt_b200 import gpu, host
 pytestmark = pytest.mark.gpu
 
 SMALL = ["tiny", "texall", "small_lights"]
+# texmaps: texall with every roughness >= 0.35 (all four texture maps, well-conditioned); *_lt: the reference's
+# ADD_LIGHT_TRIANGLE (config.h:39-47, scene.h:479-498): a 10x-intensity light triangle 0.1 behind the camera plane
+MORE = ["texmaps", "tiny_lt", "small_lights_lt"]
 
 
 @pytest.fixture(scope="module")
@@ -28,7 +31,7 @@ def rt():
     g.close()
 
 
-@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("name", SMALL + MORE)
 def test_primary_ids_vs_reference(name, rt, manifest, golden_scene):
     m = manifest["scenes"][name]
     w, h = m["width"], m["height"]
@@ -67,11 +70,14 @@ def test_upload_without_host_scene_bvh(rt, manifest, golden_scene, big_scene):
     assert gpu.lib().rt_gpu_upload_scene(rt._h, d) == -7
 
 
-@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.02), ("small_lights", 0.08), ("texall", 0.6), ("tiny_env", 0.02)])
+@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.02), ("small_lights", 0.08), ("texall", 0.6), ("tiny_env", 0.02),
+                                           ("texmaps", 0.02), ("tiny_lt", 0.02), ("small_lights_lt", 0.08)])
 def test_paths_follow_oracle(name, tol_frac, rt, manifest, golden_scene):
     """Same Philox keys -> same paths. texall contains alpha = 0.0016 near-mirrors whose GGX D term is
     ill-conditioned in float32 in the reference's own formula (1e-2 relative noise between ANY two
-    orderings), hence the loose pixel fraction there; its mean still has to agree."""
+    orderings), hence the loose pixel fraction there; its mean still has to agree.  texmaps is the same scene with
+    every roughness >= 0.35: all four texture maps, the alpha coverage and the normal-mapped frame are held to the
+    2 % bound (measured: 0.2 % of the pixels)."""
     m = manifest["scenes"][name]
     w, h = m["width"], m["height"]
     sc = golden_scene(name)
@@ -105,7 +111,7 @@ def _statistical(rt, scene, name, w, h, hi, spp):
     return err, control, mae, mae_control
 
 
-@pytest.mark.parametrize("name", ["tiny", "small_lights", "texall", "tiny_env"])
+@pytest.mark.parametrize("name", ["tiny", "small_lights", "texall", "tiny_env"] + MORE)
 def test_statistical_parity_small(name, rt, manifest, golden_scene):
     m = manifest["scenes"][name]
     w, h, hi = m["width"], m["height"], m["hi_spp"]
@@ -125,6 +131,51 @@ def test_statistical_parity_big(rt, manifest, big_scene):
     assert np.all(err < 1e-3), err
     assert np.all(err < 0.75 * control + 2e-5), (err, control)
     assert mae <= 1.0, mae
+
+
+@pytest.mark.parametrize("w,h", [(1000, 1000), (3840, 2160)])
+def test_primary_ids_at_benchmark_resolution(w, h, rt, big_scene):
+    """BASELINE configs 4 and 5 at their own resolution: the primary-hit ids of all 1 M / 8.3 M pixels against the
+    pinned oracle (bit-exact with the reference's ids on the 256 x 256 golden), north-star bound 99.9 %."""
+    from rt_b200 import gltf
+
+    sc = big_scene if w == h else gltf.load_gltf(big_scene.source_path, w / h)
+    rt.upload_scene(sc)
+    ids = rt.primary_ids(w, h)
+    ref = O.primary_ids(sc, w, h)
+    agree = (ids == ref).mean()
+    print(f"primary ids {w}x{h}: {agree * 100:.4f} % agree, {(ref >= 0).mean() * 100:.1f} % of the pixels hit geometry")
+    assert agree >= 0.999
+
+
+def test_paths_follow_oracle_at_benchmark_resolution(rt, big_scene):
+    """Config 4 at full resolution, path by path: 1000 x 1000 x 2 spp against the oracle's Philox mode (the same keys
+    give the same 2 M paths).  A pixel is off when one of its bounce decisions flipped on a last-ulp difference; on
+    this scene (bumpy walls, grazing rays) that is 7 % of the pixels at 2 spp on the host compilation of the device
+    math as well."""
+    w = h = 1000
+    spp, seed = 2, 5
+    rt.upload_scene(big_scene)
+    rt.render(w, h, spp, seed=seed)
+    img, st = rt.readback()
+    ref, ost = O.render(big_scene, w, h, spp, rng_mode=O.RNG_PHILOX, seed=seed)
+    rel = (np.abs(img - ref) / (np.abs(ref) + 1e-3)).max(axis=2)
+    off = (rel > 1e-3).mean()
+    print(f"1000x1000x2 spp: {off * 100:.2f} % of the pixels off by > 1e-3, median relative difference {np.median(rel):.2e}")
+    assert off <= 0.12 and np.median(rel) < 2e-4
+    assert abs(img.mean() - ref.mean()) < 2e-3 * ref.mean()
+    assert st["samples"] == ost["samples"] == w * h * spp
+    # Work counters: the GPU traces 0.4 % MORE extension rays than the oracle here, systematically.  Traced to its cause
+    # on the host compilation of the device math (per-pixel ray counts, DESIGN.md section 5): a light-sampled direction
+    # towards an emissive panel that is coplanar with the wall just hit has dot(dir, Ns) == 0 EXACTLY in the reference's
+    # arithmetic whenever its hit point rounds onto the plane (x = o + d * t, two roundings), which ends the path
+    # (`scl == 0`, raytracer.h:584-586); the device forms the hit point with one fused multiply-add and lands an ulp
+    # beside the plane, so the same path goes on with a weight of ~1e-14.  No radiance is involved.
+    assert abs(st["extension_rays"] - ost["extension_rays"]) <= 1e-2 * ost["extension_rays"]
+    # light-pdf traversals: the reference also evaluates bvh_mix_dist::pdf at the LAST bounce, whose continuation is
+    # trace_ray(depth 0) = 0 (raytracer.h:572-574, 596-598); the device skips that traversal (2.3 % of them here)
+    assert -4e-2 * ost["light_pdf_rays"] <= st["light_pdf_rays"] - ost["light_pdf_rays"] <= 0
+    assert abs(st["shades"] - ost["shades"]) <= 1e-2 * ost["shades"]
 
 
 def test_determinism_and_sample_split(rt, golden_scene):
@@ -274,6 +325,36 @@ def test_cli_drop_in_matches_reference_binary(scene_dir, tmp_path):
             assert img.shape == ref.shape
             mae = np.abs(img.astype(int) - ref.astype(int)).mean()
             assert mae < 1.0, (name, mae)  # tiny scene: 0.52 LSB reference-vs-reference at 4096 spp
+
+
+def test_cli_extra_light_triangle_switch(scene_dir, tmp_path, manifest):
+    """RT_ADD_LIGHT_TRIANGLE=1 is the run-time form of the reference's compile-time ADD_LIGHT_TRIANGLE (config.h:39-47):
+    both CLIs append the light the reference's loader would (scene.h:479-498); their PPMs match the tonemapped
+    16 384-spp render of the unmodified reference with that light (tests/golden/tiny_lt_refhi_a.f32)."""
+    import subprocess
+    from conftest import ROOT
+    from rt_b200 import cli
+
+    m = manifest["scenes"]["tiny_lt"]
+    w, h = m["width"], m["height"]
+    ref = host.tonemap_rgb8(golden_array("tiny_lt_refhi_a.f32", np.float32, (h, w, 3)))
+    plain = host.tonemap_rgb8(golden_array("tiny_refhi_a.f32", np.float32, (h, w, 3)))
+    assert np.abs(ref.astype(int) - plain.astype(int)).mean() > 5  # the extra light changes the image visibly
+    exe = os.path.join(ROOT, "bin", "raytracer_b200")
+    env = dict(os.environ, RT_ADD_LIGHT_TRIANGLE="1")
+    outs = {}
+    os.environ["RT_ADD_LIGHT_TRIANGLE"] = "1"
+    try:
+        assert cli.main(["prog", scene_dir("tiny"), str(w), str(h), "8192", str(tmp_path / "py.ppm")]) == 0
+    finally:
+        del os.environ["RT_ADD_LIGHT_TRIANGLE"]
+    outs["python"] = _read_ppm(tmp_path / "py.ppm")
+    if os.path.exists(exe):
+        subprocess.run([exe, scene_dir("tiny"), str(w), str(h), "8192", str(tmp_path / "cxx.ppm")], check=True, env=env)
+        outs["cxx"] = _read_ppm(tmp_path / "cxx.ppm")
+    for name, img in outs.items():
+        mae = np.abs(img.astype(int) - ref.astype(int)).mean()
+        assert mae < 1.0, (name, mae)
 
 
 def test_cli_drop_in_accepts_course_text_scenes(tmp_path):

@@ -73,6 +73,33 @@ def test_python_loader_and_bvh_build_match_reference_flattening(name, scene_dir,
     assert_same_scene(golden_scene(name), mine)
 
 
+def test_texmaps_loader_matches_reference_flattening(scene_dir, manifest, golden_scene):
+    m = manifest["scenes"]["texmaps"]
+    assert_same_scene(golden_scene("texmaps"), gltf.load_gltf(scene_dir("texmaps"), m["width"] / m["height"]))
+
+
+@pytest.mark.parametrize("name", ["tiny_lt", "small_lights_lt"])
+def test_extra_light_triangle_matches_reference_flattening(name, scene_dir, manifest, golden_scene):
+    """ADD_LIGHT_TRIANGLE (config.h:39-47, false at HEAD): the object parse_gltf_scene appends under that switch
+    (scene.h:479-498) — the Python loader's run-time form of it reproduces the reference's flattened scene bit for bit
+    (positions, its own normal, default material with emission 10, both BVHs with the triangle in them)."""
+    m = manifest["scenes"][name]
+    ref = golden_scene(name)
+    base = golden_scene(m["base"])
+    mine = gltf.load_gltf(scene_dir(m["base"]), m["width"] / m["height"], add_light_triangle=True)
+    assert_same_scene(ref, mine)
+    assert ref.n_tris == base.n_tris + 1 and len(ref.light_bvh.objects) == len(base.light_bvh.objects) + 1
+    lt = ref.tri_pos[-1]
+    cam_z = (lt - ref.camera_position) @ ref.camera_forward
+    assert np.allclose(cam_z, -0.1, atol=1e-5)  # 0.1 behind the camera plane
+    assert np.all(ref.materials[ref.tri_material[-1]]["emission"] == 10.0)
+    os.environ["RT_ADD_LIGHT_TRIANGLE"] = "1"  # the environment switch of the CLIs
+    try:
+        assert_same_scene(ref, gltf.load_gltf(scene_dir(m["base"]), m["width"] / m["height"]))
+    finally:
+        del os.environ["RT_ADD_LIGHT_TRIANGLE"]
+
+
 def test_environment_map_loader_matches_reference_flattening(scene_dir, manifest, golden_scene):
     """Scene::bg as an equirectangular texture (main.cpp:29-31): the Python loader appends it exactly like the
     reference-hosted flattener; the RTSC container carries env_texture."""
@@ -480,7 +507,8 @@ def test_device_math_follows_oracle_paths_eight_wide(name, tol_frac, hc, manifes
 
 
 @pytest.mark.parametrize("rebuild", [0, 1])
-@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.01), ("small_lights", 0.02), ("tiny_env", 0.01)])
+@pytest.mark.parametrize("name,tol_frac", [("tiny", 0.01), ("small_lights", 0.02), ("tiny_env", 0.01), ("texmaps", 0.01),
+                                           ("tiny_lt", 0.01), ("small_lights_lt", 0.04)])
 def test_device_math_follows_oracle_paths(name, tol_frac, rebuild, hc, manifest, golden_scene):
     """Same Philox keys -> same paths: per-pixel means agree to float noise for all but the few pixels where a
     rounding difference flipped a discrete decision.  `rebuild`: with the library's own SAH tree instead of the
