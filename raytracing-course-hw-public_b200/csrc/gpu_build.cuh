@@ -161,7 +161,6 @@ __global__ void __launch_bounds__(256) kb_setup(Arrays A) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {HUGE_VALF, HUGE_VALF, HUGE_VALF}, hi[3] = {-HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
     float cl[3] = {HUGE_VALF, HUGE_VALF, HUGE_VALF}, ch[3] = {-HUGE_VALF, -HUGE_VALF, -HUGE_VALF};
-    bool tangent = false;
     if (i < A.n) {
         const float *p = A.tri_pos + static_cast<size_t>(i) * 9;
         bool finite = true;
@@ -178,13 +177,20 @@ __global__ void __launch_bounds__(256) kb_setup(Arrays A) {
         A.idx[0][i] = i;
         A.node_of[0][i] = 0;
         A.last[i] = 0;
-        if (A.tri_tangents) {
-            const float *t = A.tri_tangents + static_cast<size_t>(i) * 9;
-            for (int v = 0; v < 3; ++v) tangent = tangent || !(t[v * 3] == 1.0f && t[v * 3 + 1] == 0.0f && t[v * 3 + 2] == 0.0f);
-        }
     }
     warp_minmax_atomic(A.c->root_box, lo, hi);
     warp_minmax_atomic(A.c->root_cb, cl, ch);
+}
+
+// does any tangent differ from the loader's default (1,0,0)?  (The reference's loader never finds a tangent attribute,
+// scene.h:336, so hosts pass n x 9 default floats; DTangent is only built when it matters.)
+__global__ void __launch_bounds__(256) kb_tangent_flag(Arrays A) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool tangent = false;
+    if (i < A.n && A.tri_tangents) {
+        const float *t = A.tri_tangents + static_cast<size_t>(i) * 9;
+        for (int v = 0; v < 3; ++v) tangent = tangent || !(t[v * 3] == 1.0f && t[v * 3 + 1] == 0.0f && t[v * 3 + 2] == 0.0f);
+    }
     if (__any_sync(0xFFFFFFFFu, tangent) && (threadIdx.x & 31) == 0) atomicOr(&A.c->any_tangent, 1u);
 }
 

@@ -116,6 +116,8 @@ struct DeviceState {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the triangle attributes while the BVH build runs on `stream`
+    cudaEvent_t ev_copied = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
     // scene
     DevBuf<QNode4> qnodes4, lqnodes4;  // scene BVH and light BVH, 4-wide quantised (both traversed by k_extend)
@@ -223,17 +225,22 @@ int device_build_scene(DeviceState &d, const rt_scene_desc &sc, double *t_h2d_ms
     CU_CHECK(cudaSetDevice(d.device));
     const uint32_t n = sc.n_tris;
     const auto t0 = std::chrono::steady_clock::now();
-    auto h2d = [&](auto &buf, const auto *src, size_t count) -> int {
+    // The build needs the positions only; normals, uv, materials and tangents (3/4 of the bytes) are copied on a second
+    // stream while it runs and are waited for before they are first read (from pinned host memory the copies are real
+    // DMA and overlap; from pageable memory cudaMemcpyAsync stages synchronously and nothing is lost).
+    auto h2d = [&](auto &buf, const auto *src, size_t count, cudaStream_t on) -> int {
         if (int rc = buf.alloc(std::max<size_t>(count, 1))) return rc;
-        if (count) CU_CHECK(cudaMemcpyAsync(buf.p, src, count * sizeof(*src), cudaMemcpyHostToDevice, d.stream));
+        if (count) CU_CHECK(cudaMemcpyAsync(buf.p, src, count * sizeof(*src), cudaMemcpyHostToDevice, on));
         return RT_OK;
     };
-    if (int rc = h2d(d.in_pos, sc.tri_pos, static_cast<size_t>(n) * 9)) return rc;
-    if (int rc = h2d(d.in_nrm, sc.tri_normals, static_cast<size_t>(n) * 9)) return rc;
-    if (int rc = h2d(d.in_uv, sc.tri_uv, static_cast<size_t>(n) * 6)) return rc;
-    if (int rc = h2d(d.in_mat, sc.tri_material, static_cast<size_t>(n))) return rc;
+    if (int rc = h2d(d.in_pos, sc.tri_pos, static_cast<size_t>(n) * 9, d.stream)) return rc;
+    // (the previous render's kernels on d.stream may still read nothing of these buffers: rt_gpu_render is synchronous)
+    if (int rc = h2d(d.in_nrm, sc.tri_normals, static_cast<size_t>(n) * 9, d.copy_stream)) return rc;
+    if (int rc = h2d(d.in_uv, sc.tri_uv, static_cast<size_t>(n) * 6, d.copy_stream)) return rc;
+    if (int rc = h2d(d.in_mat, sc.tri_material, static_cast<size_t>(n), d.copy_stream)) return rc;
     if (sc.tri_tangents)
-        if (int rc = h2d(d.in_tan, sc.tri_tangents, static_cast<size_t>(n) * 9)) return rc;
+        if (int rc = h2d(d.in_tan, sc.tri_tangents, static_cast<size_t>(n) * 9, d.copy_stream)) return rc;
+    CU_CHECK(cudaEventRecord(d.ev_copied, d.copy_stream));
     if (t_h2d_ms) *t_h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
     // scratch carved from one allocation
@@ -340,9 +347,15 @@ int device_build_scene(DeviceState &d, const rt_scene_desc &sc, double *t_h2d_ms
     const uint32_t g_split = static_cast<uint32_t>((n_pool + 3) / 4);  // one warp per node
     int parity = 0;
     uint32_t level = 0;
+    bool attrs_joined = false;
     for (;; ++level) {
         if (level >= RT_STACK_SIZE) return fail(RT_ERR_CUDA, "device BVH build did not terminate");
         if (static_cast<int>(level) >= first_check && ((level - first_check) & 1u) == 0) {
+            if (!attrs_joined) {  // the attribute copies have had the top levels' time; the tangent flag rides on this fetch
+                CU_CHECK(cudaStreamWaitEvent(st, d.ev_copied, 0));
+                if (sc.tri_tangents) kb_tangent_flag<<<g_n, 256, 0, st>>>(A);
+                attrs_joined = true;
+            }
             if (int rc = fetch_counters()) return rc;
             if (hc.n_active[level & 1] == 0) break;
         }
@@ -672,6 +685,8 @@ int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
                                               "' is not sm_100+ (kernels are built for sm_100a only)");
         d->sm_count = prop.multiProcessorCount;
         CU_CHECK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
         CU_CHECK(cudaEventCreate(&d->ev_begin));
         CU_CHECK(cudaEventCreate(&d->ev_end));
         CU_CHECK(cudaEventCreate(&d->ev_red0));
@@ -747,6 +762,8 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         for (cudaEvent_t e : d.event_pool) cudaEventDestroy(e);
         for (cudaEvent_t e : {d.ev_begin, d.ev_end, d.ev_red0, d.ev_red1})
             if (e) cudaEventDestroy(e);
+        if (d.ev_copied) cudaEventDestroy(d.ev_copied);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     cudaGetLastError();
