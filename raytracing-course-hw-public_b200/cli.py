@@ -14,7 +14,8 @@ def run_raytracer(scene, width, height, samples, seed=0, n_gpus=1):
             rt.upload_text_scene(scene)
         else:
             rt.upload_scene(scene)
-        rt.render(width, height, samples, seed=seed)
+        # one-shot command: 128 Mi paths per batch (17 GB of queues instead of 68 GB), see host/main_ref_host.cpp
+        rt.render(width, height, samples, seed=seed, max_paths_in_flight=int(os.environ.get("RT_PATHS", 128 << 20)))
         return rt.readback()
 
 

@@ -43,6 +43,36 @@ RT_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RT_HD f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 RT_HD float len2(f3 a) { return dot(a, a); }
 RT_HD f3 normalize(f3 a) { return a * (1.0f / sqrtf(len2(a))); }  // geometry::norm, geometry.h:31-34
+// normalize_dir: for vectors that do NOT feed the GGX D term (geometric normal, sampled directions before the final
+// half-vector): MUFU.RSQ instead of IEEE sqrt + division (a third of the instructions; `normalize` was 14 % of k_shade's).
+// Everything the D term sees (shading normal, half vector, VNDF frame) keeps the IEEE form: with alpha = 0.0016
+// near-mirrors D = alpha^2 / (pi (1 - ndh^2 + alpha^2 ndh^2)^2) amplifies a 1e-7 length error of ns or h to 10 % of D, and
+// rsqrt everywhere biased the texall golden by 0.7 % at 131 072 spp (profiles/r2_normalize.md).
+#if defined(__CUDA_ARCH__) && (!defined(RT_FAST_NORMALIZE) || RT_FAST_NORMALIZE)
+RT_HD f3 normalize_dir(f3 a) { return a * rsqrtf(len2(a)); }
+#else
+RT_HD f3 normalize_dir(f3 a) { return normalize(a); }
+#endif
+// The same trade for the well-conditioned scalar divisions and square roots of the samplers, pdfs and the BRDF (MUFU.RCP /
+// MUFU.SQRT, 1-2 ulp, instead of the IEEE sequences of ~9 instructions each): a relative error of 2e-7 in a factor of the
+// estimator.  The host compilation (tests/hostcheck) keeps the IEEE forms.
+#if defined(__CUDA_ARCH__) && (!defined(RT_FAST_SHADE_MATH) || RT_FAST_SHADE_MATH)
+RT_HD float sh_div(float a, float b) { return __fdividef(a, b); }
+RT_HD float sh_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+RT_HD float sh_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#else
+RT_HD float sh_div(float a, float b) { return a / b; }
+RT_HD float sh_rcp(float x) { return 1.0f / x; }
+RT_HD float sh_sqrt(float x) { return sqrtf(x); }
+#endif
 RT_HD bool any_nan(f3 a) { return (a.x != a.x) || (a.y != a.y) || (a.z != a.z); }
 
 #define RT_PI 3.14159265358979323846f
@@ -804,7 +834,7 @@ RT_HD Surface make_surface(const DScene &s, const float *lut, const Hit &h, f3 d
     const f8 aa = ld8(ap), ab = ld8(ap + 32);
     const f4 a0 = f4{aa.a, aa.b, aa.c, aa.d}, a1 = f4{aa.e, aa.f, aa.g, aa.h};
     const f4 a2 = f4{ab.a, ab.b, ab.c, ab.d}, a3 = f4{ab.e, ab.f, ab.g, ab.h};
-    f3 ng = normalize(cross(mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z)));  // Object::base_normal
+    f3 ng = normalize_dir(cross(mk3(t1.x, t1.y, t1.z), mk3(t2.x, t2.y, t2.z)));  // Object::base_normal
     const bool inside = dot(ng, dir) > 0.0f;                                   // bvh.h:92
     const float w0 = 1.0f - h.b - h.c;                                         // triangle::interop, geometry.h:497-502
     f3 smooth = normalize(mk3(a0.x, a0.y, a0.z) * w0 + mk3(a1.x, a1.y, a1.z) * h.b + mk3(a2.x, a2.y, a2.z) * h.c);
@@ -875,61 +905,61 @@ RT_HD void sincos_2pi(float u, float &s, float &c) {  // sin/cos(2*pi*u)
 RT_HD f3 choose_local_x(f3 n) {  // VNDF_dist::choose_local_x, raytracer.h:208-219
     f3 r = mk3(1.0f, 1.0f, 1.0f);
     const float dn = n.x + n.y + n.z;
-    if (fabsf(n.x) > 0.5f) r.x -= dn / n.x;
-    else if (fabsf(n.y) > 0.5f) r.y -= dn / n.y;
-    else r.z -= dn / n.z;
+    // one well-conditioned division (|n.k| > 0.5, or the largest component): MUFU.RCP leaves the frame orthogonal to
+    // 2e-7 instead of 6e-8; the normalisation stays IEEE (the frame feeds the D term of vndf_pdf)
+    if (fabsf(n.x) > 0.5f) r.x -= sh_div(dn, n.x);
+    else if (fabsf(n.y) > 0.5f) r.y -= sh_div(dn, n.y);
+    else r.z -= sh_div(dn, n.z);
     return normalize(r);
 }
 
 // VNDF_dist::sample (Heitz 2018), raytracer.h:140-173. alpha = max(roughness, MIN_ROUGHNESS)^2.
-RT_HD f3 vndf_sample(float alpha, f3 in_dir, f3 ns, float u1, float u2) {
-    const f3 nx = choose_local_x(ns);
+RT_HD f3 vndf_sample(float alpha, f3 in_dir, f3 ns, f3 nx, float u1, float u2) {  // nx = choose_local_x(ns)
     const f3 ny = cross(ns, nx);
-    const f3 v = -normalize(mk3(dot(nx, in_dir), dot(ny, in_dir), dot(ns, in_dir)));
-    const f3 vh = normalize(mk3(alpha * v.x, alpha * v.y, v.z));
+    const f3 v = -normalize_dir(mk3(dot(nx, in_dir), dot(ny, in_dir), dot(ns, in_dir)));
+    const f3 vh = normalize_dir(mk3(alpha * v.x, alpha * v.y, v.z));
     const float lensq = vh.x * vh.x + vh.y * vh.y;
-    const f3 T1 = lensq > 0.0f ? mk3(-vh.y, vh.x, 0.0f) * (1.0f / sqrtf(lensq)) : mk3(1.0f, 0.0f, 0.0f);
+    const f3 T1 = lensq > 0.0f ? mk3(-vh.y, vh.x, 0.0f) * sh_rcp(sh_sqrt(lensq)) : mk3(1.0f, 0.0f, 0.0f);
     const f3 T2 = cross(vh, T1);
-    const float r = sqrtf(u1);
+    const float r = sh_sqrt(u1);
     float sp, cp;
     sincos_2pi(u2, sp, cp);
     const float t1 = r * cp;
     float t2 = r * sp;
     const float sh = 0.5f * (1.0f + vh.z);
-    t2 = (1.0f - sh) * sqrtf(1.0f - t1 * t1) + sh * t2;
-    const float t3 = sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
+    t2 = (1.0f - sh) * sh_sqrt(1.0f - t1 * t1) + sh * t2;
+    const float t3 = sh_sqrt(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2));
     const f3 nh = t1 * T1 + t2 * T2 + t3 * vh;
-    const f3 ne = normalize(mk3(alpha * nh.x, alpha * nh.y, fmaxf(0.0f, nh.z)));
-    const f3 res_n = normalize(ne.x * nx + ne.y * ny + ne.z * ns);
+    const f3 ne = normalize_dir(mk3(alpha * nh.x, alpha * nh.y, fmaxf(0.0f, nh.z)));
+    const f3 res_n = normalize_dir(ne.x * nx + ne.y * ny + ne.z * ns);  // the half vector is re-normalised (IEEE) by the caller
     return in_dir - res_n * (2.0f * dot(in_dir, res_n));  // geometry::reflect
 }
 
 // VNDF_dist::pdf, raytracer.h:175-206
-RT_HD float vndf_pdf(float alpha, float eps, f3 in_dir, f3 ns, f3 dir) {
-    const f3 nx = choose_local_x(ns);
+// nx = choose_local_x(ns), hw = normalize(dir - in_dir): both are shared with the sampler / the BRDF by the caller
+RT_HD float vndf_pdf(float alpha, float eps, f3 in_dir, f3 ns, f3 nx, f3 hw) {
     const f3 ny = cross(ns, nx);
     const f3 v = -mk3(dot(nx, in_dir), dot(ny, in_dir), dot(ns, in_dir));
-    const f3 hw = normalize(dir - in_dir);
     const f3 n = mk3(dot(nx, hw), dot(ny, hw), dot(ns, hw));
     const float vdn = dot(v, n);
     if (!(vdn > 0.0f)) return 0.0f;
     const float ax = v.x * alpha, ay = v.y * alpha;
-    const float lambda = (-1.0f + sqrtf(1.0f + (ax * ax + ay * ay) / (v.z * v.z))) * 0.5f;
-    const float g1 = 1.0f / (1.0f + lambda);
-    const float nxa = n.x / alpha, nya = n.y / alpha;
+    const float lambda = (-1.0f + sh_sqrt(1.0f + sh_div(ax * ax + ay * ay, v.z * v.z))) * 0.5f;
+    const float g1 = sh_rcp(1.0f + lambda);
+    const float nxa = sh_div(n.x, alpha), nya = sh_div(n.y, alpha);
     const float q = nxa * nxa + nya * nya + n.z * n.z;
-    const float dn = RT_INV_PI / (alpha * alpha * q * q);
+    const float dn = sh_div(RT_INV_PI, alpha * alpha * q * q);
     // g1 * vdn * dn / max(eps, v.z) / 4 / vdn
-    return g1 * vdn * dn / fmaxf(eps, v.z) * 0.25f / vdn;
+    return sh_div(sh_div(g1 * vdn * dn, fmaxf(eps, v.z)) * 0.25f, vdn);
 }
 
 // cosine_dist::sample = norm(n + uniform_sphere), sphere from z in U[-1,1], phi in U[0,2pi) (raytracer.h:94-121)
 RT_HD f3 cosine_sample(f3 ng, float u1, float u2) {
     const float z = u1 * 2.0f - 1.0f;
-    const float cz = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    const float cz = sh_sqrt(fmaxf(0.0f, 1.0f - z * z));
     float sp, cp;
     sincos_2pi(u2, sp, cp);
-    return normalize(ng + mk3(cz * cp, cz * sp, z));
+    return normalize_dir(ng + mk3(cz * cp, cz * sp, z));
 }
 RT_HD float cosine_pdf(f3 ng, f3 dir) { return fmaxf(dot(ng, dir) * RT_INV_PI, 0.0f); }  // raytracer.h:123-128
 
@@ -945,7 +975,7 @@ RT_HD f3 light_sample(const DScene &s, f3 x, float u_index, float u, float v) {
         v = 1.0f - v;
     }
     const f3 pt = mk3(t0.x, t0.y, t0.z) + mk3(t1.x, t1.y, t1.z) * v + mk3(t2.x, t2.y, t2.z) * u;
-    return normalize(pt - x);
+    return normalize_dir(pt - x);
 }
 
 RT_HD float pow5(float x) {
@@ -958,22 +988,21 @@ RT_HD float specular_brdf(float alpha, f3 in_dir, f3 out_dir, f3 ns, f3 h) {
     const float a2 = alpha * alpha;
     const float ndh = dot(ns, h);
     const float dd = ndh * ndh * (a2 - 1.0f) + 1.0f;
-    const float d = (ndh > 0.0f ? a2 : 0.0f) * RT_INV_PI / (dd * dd);
+    const float d = sh_div((ndh > 0.0f ? a2 : 0.0f) * RT_INV_PI, dd * dd);  // the division is well-conditioned; dd is not (normalize)
     const float ndo = dot(ns, out_dir), ndi = -dot(ns, in_dir);
-    const float div1 = fabsf(ndo) + sqrtf(a2 + (1.0f - a2) * ndo * ndo);
-    const float div2 = fabsf(ndi) + sqrtf(a2 + (1.0f - a2) * ndi * ndi);
-    const float vis = (dot(h, out_dir) > 0.0f && -dot(h, in_dir) > 0.0f) ? 1.0f / (div1 * div2) : 0.0f;
+    const float div1 = fabsf(ndo) + sh_sqrt(a2 + (1.0f - a2) * ndo * ndo);
+    const float div2 = fabsf(ndi) + sh_sqrt(a2 + (1.0f - a2) * ndi * ndi);
+    const float vis = (dot(h, out_dir) > 0.0f && -dot(h, in_dir) > 0.0f) ? sh_rcp(div1 * div2) : 0.0f;
     return vis * d;
 }
 
 // pbr_brdf, raytracer.h:295-343: (1-m) * mix(diffuse c/pi, spec, F(ior)) + m * spec * (c + (1-c) F5)
-RT_HD f3 pbr_brdf(const Surface &sf, float alpha, f3 in_dir, f3 out_dir) {
-    const f3 h = normalize(out_dir - in_dir);  // halfway, raytracer.h:131-134
+RT_HD f3 pbr_brdf(const Surface &sf, float alpha, f3 in_dir, f3 out_dir, f3 h) {  // h = halfway, raytracer.h:131-134
     const float spec = specular_brdf(alpha, in_dir, out_dir, sf.ns, h);
     const float p5 = pow5(1.0f - fabsf(dot(-in_dir, h)));
     f3 res = mk3(0.0f, 0.0f, 0.0f);
     if (sf.metallic < 1.0f) {
-        const float r0 = (1.0f - sf.ior) / (1.0f + sf.ior);
+        const float r0 = sh_div(1.0f - sf.ior, 1.0f + sf.ior);
         const float f0 = r0 * r0;
         const float fr = f0 + (1.0f - f0) * p5;
         const f3 diel = sf.color * (RT_INV_PI * (1.0f - fr)) + mk3(spec, spec, spec) * fr;
@@ -998,6 +1027,7 @@ RT_HD f3 pbr_brdf(const Surface &sf, float alpha, f3 in_dir, f3 out_dir) {
 struct ShadeMid {
     Surface sf;
     f3 pos, dir;
+    f3 nx;  // VNDF frame axis choose_local_x(ns): one evaluation serves the sampler and the pdf
     float alpha;
 };
 enum ShadeStep { SHADE_END = 0, SHADE_PASS = 1, SHADE_SAMPLED = 2 };
@@ -1023,8 +1053,9 @@ RT_HD ShadeStep shade_begin(const DScene &s, const float *lut, const RngKey &key
     if (last_bounce) return SHADE_END;            // trace_ray(depth 0) = 0, raytracer.h:596-598
     const float rough = fmaxf(mid.sf.roughness, s.min_roughness);
     mid.alpha = rough * rough;
+    mid.nx = choose_local_x(mid.sf.ns);
     if (u01(r0.y) <= s.vndf_factor) {
-        mid.dir = vndf_sample(mid.alpha, d, mid.sf.ns, u01(r0.z), u01(r0.w));
+        mid.dir = vndf_sample(mid.alpha, d, mid.sf.ns, mid.nx, u01(r0.z), u01(r0.w));
     } else {
         const u4 r1 = rng_block(key, bounce, 1);
         // mix_dist{cosine, bvh_mix}: uniform selector, raytracer.h:383-392; cosine only without lights (:449-453)
@@ -1051,11 +1082,12 @@ struct ShadeWeights {
 };
 RT_HD ShadeWeights shade_weights(const DScene &s, const ShadeMid &mid, f3 d_in) {
     ShadeWeights w;
-    const float p_vndf = vndf_pdf(mid.alpha, s.eps, d_in, mid.sf.ns, mid.dir);
+    const f3 h = normalize(mid.dir - d_in);  // halfway (raytracer.h:131-134): one IEEE normalisation for the pdf and the BRDF
+    const float p_vndf = vndf_pdf(mid.alpha, s.eps, d_in, mid.sf.ns, mid.nx, h);
     const float p_cos = cosine_pdf(mid.sf.ng, mid.dir);
     const float k = s.n_lights > 0 ? 0.5f : 1.0f;  // mix_dist::pdf = mean of the sub-pdfs, raytracer.h:395-407
     w.p_partial = s.vndf_factor * p_vndf + (1.0f - s.vndf_factor) * k * p_cos;
-    w.f_cos = pbr_brdf(mid.sf, mid.alpha, d_in, mid.dir) * fmaxf(0.0f, dot(mid.dir, mid.sf.ns));
+    w.f_cos = pbr_brdf(mid.sf, mid.alpha, d_in, mid.dir, h) * fmaxf(0.0f, dot(mid.dir, mid.sf.ns));
     return w;
 }
 RT_HD float light_pdf_weight(const DScene &s) { return s.n_lights > 0 ? (1.0f - s.vndf_factor) * 0.5f : 0.0f; }
@@ -1064,7 +1096,7 @@ RT_HD float light_pdf_weight(const DScene &s) { return s.n_lights > 0 ? (1.0f - 
 RT_HD bool shade_resolve(const DScene &s, f3 thr_f, float p_partial, float p_light, f3 &thr) {
     const float p = p_partial + light_pdf_weight(s) * p_light;
     if (p < s.eps) return false;  // NaN p continues, like the reference
-    const f3 scaled = thr_f * (1.0f / p);
+    const f3 scaled = thr_f * sh_rcp(p);
     if (len2(scaled) == 0.0f) return false;
     thr = scaled;
     return true;
