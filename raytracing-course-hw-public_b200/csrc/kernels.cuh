@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                                 const f3 xy = d * t;  // y - x
                                 const float d2 = len2(xy);
                                 const f3 w = xy * rsqrtf(d2);
-                                lsum += d2 / (fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);
+                                lsum += __fdividef(d2, fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);  // MUFU.RCP: 2e-7 of a pdf term
                             } else {
                                 best_t = t;
                                 best_b = beta;
