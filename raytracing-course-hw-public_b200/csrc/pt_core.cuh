@@ -349,13 +349,30 @@ RT_HD Hit closest_hit_q(const DBvh &bvh, f3 o, f3 d, float min_dst, uint32_t *st
 struct Node4Test {
     float d[4];
 };
-template <int C> RT_HD float q4_entry(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float ax,
-                                      float bx, float ay, float by, float az, float bz, uint32_t one, float eps, float best_t) {
-    const float entry = fmaxf(fmaxf(fmaxf(fmaf(qplane<C>(nx, one), ax, bx), fmaf(qplane<C>(ny, one), ay, by)),
-                                    fmaf(qplane<C>(nz, one), az, bz)), eps);
-    const float exit_ = fminf(fminf(fminf(fmaf(qplane<C>(fx, one), ax, bx), fmaf(qplane<C>(fy, one), ay, by)),
-                                    fmaf(qplane<C>(fz, one), az, bz)), best_t);
-    return entry <= exit_ ? entry : INFINITY;
+// RT_EXT_FFMA2 (device only): the 24 plane evaluations of a node step as 12 packed FFMA2 (fma.rn.f32x2, sm_100+: two
+// IEEE fused multiply-adds per instruction with the scale and offset as broadcast scalar operands) — the same 24
+// results bit for bit, half the FMA issue slots of the slab tests.
+#ifndef RT_EXT_FFMA2
+#define RT_EXT_FFMA2 1
+#endif
+// the four plane distances of one plane word: t[c] = fma(1 + byte_c(w) * 2^-16, a, b)
+RT_HD void q4_axis(uint32_t w, float a, float b, uint32_t one, float t[4]) {
+#if defined(__CUDA_ARCH__) && RT_EXT_FFMA2
+    unsigned long long q01, q23, r01, r23, aa, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q01) : "f"(qplane<0>(w, one)), "f"(qplane<1>(w, one)));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(q23) : "f"(qplane<2>(w, one)), "f"(qplane<3>(w, one)));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r01) : "l"(q01), "l"(aa), "l"(bb));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r23) : "l"(q23), "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t[0]), "=f"(t[1]) : "l"(r01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t[2]), "=f"(t[3]) : "l"(r23));
+#else
+    t[0] = fmaf(qplane<0>(w, one), a, b);
+    t[1] = fmaf(qplane<1>(w, one), a, b);
+    t[2] = fmaf(qplane<2>(w, one), a, b);
+    t[3] = fmaf(qplane<3>(w, one), a, b);
+#endif
 }
 RT_HD Node4Test qnode4_test(const uint32_t ox, const uint32_t oy, const uint32_t oz, const uint32_t lox, const uint32_t loy,
                             const uint32_t loz, const uint32_t hix, const uint32_t hiy, const uint32_t hiz, f3 idir, f3 ood,
@@ -367,11 +384,22 @@ RT_HD Node4Test qnode4_test(const uint32_t ox, const uint32_t oy, const uint32_t
     const uint32_t nx = px ? lox : hix, fx = px ? hix : lox;
     const uint32_t ny = py ? loy : hiy, fy = py ? hiy : loy;
     const uint32_t nz = pz ? loz : hiz, fz = pz ? hiz : loz;
+    float tnx[4], tny[4], tnz[4], tfx[4], tfy[4], tfz[4];
+    q4_axis(nx, ax, bx, one, tnx);
+    q4_axis(ny, ay, by, one, tny);
+    q4_axis(nz, az, bz, one, tnz);
+    q4_axis(fx, ax, bx, one, tfx);
+    q4_axis(fy, ay, by, one, tfy);
+    q4_axis(fz, az, bz, one, tfz);
     Node4Test r;
-    r.d[0] = q4_entry<0>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
-    r.d[1] = q4_entry<1>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
-    r.d[2] = q4_entry<2>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
-    r.d[3] = q4_entry<3>(nx, ny, nz, fx, fy, fz, ax, bx, ay, by, az, bz, one, eps, best_t);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 4; ++c) {
+        const float entry = fmaxf(fmaxf(fmaxf(tnx[c], tny[c]), tnz[c]), eps);
+        const float exit_ = fminf(fminf(fminf(tfx[c], tfy[c]), tfz[c]), best_t);
+        r.d[c] = entry <= exit_ ? entry : INFINITY;
+    }
     return r;
 }
 // compare-exchange of (distance, link) pairs, ascending by distance; equal distances keep their order (ties: lower

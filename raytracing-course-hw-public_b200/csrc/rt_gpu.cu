@@ -697,6 +697,9 @@ int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
         int occ_e = 0, occ_s = 0;
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, RT_K_EXTEND, rt::kExtendThreads, 0));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, rt::k_shade, rt::kShadeThreads, 0));
+        // experiment knobs: resident CTAs per SM of the two persistent kernels (default: all that fit)
+        if (const char *e = std::getenv("RT_EXT_CTAS_PER_SM")) occ_e = std::min(occ_e, std::max(1, std::atoi(e)));
+        if (const char *e = std::getenv("RT_SHADE_CTAS_PER_SM")) occ_s = std::min(occ_s, std::max(1, std::atoi(e)));
         d->extend_blocks = d->sm_count * std::max(occ_e, 1);
         d->shade_blocks = d->sm_count * std::max(occ_s, 1);
     }
