@@ -173,6 +173,45 @@ __device__ __forceinline__ float rcp_rn(float x) {
     return r;
 }
 
+// L1 eviction hints of k_extend's scene fetches: 0 none, 1 no_allocate, 2 evict_last, 3 evict_first.  Triangles are
+// read about once per ray and from a 16 MB array; nodes are re-read (the top of the tree by every ray).
+#ifndef RT_EXT_NODE_L1
+#define RT_EXT_NODE_L1 0
+#endif
+#ifndef RT_EXT_TRI_L1
+#define RT_EXT_TRI_L1 1  // no_allocate: k_extend 159.5 -> 157.3 ms per 256 spp (evict_first: no change; evict_last on the nodes: +1 %)
+#endif
+#ifndef RT_EXT_SPLIT_NODES
+#define RT_EXT_SPLIT_NODES 1  // node halves from two arrays of 32-byte stride (DBvh::q4lo) instead of 64-byte records
+#endif
+template <int H> __device__ __forceinline__ f8 ld8h(const void *p) {
+    f8 v;
+    if (H == 1)
+        asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(v.a), "=f"(v.b), "=f"(v.c), "=f"(v.d), "=f"(v.e), "=f"(v.f), "=f"(v.g), "=f"(v.h) : "l"(p));
+    else if (H == 2)
+        asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(v.a), "=f"(v.b), "=f"(v.c), "=f"(v.d), "=f"(v.e), "=f"(v.f), "=f"(v.g), "=f"(v.h) : "l"(p));
+    else if (H == 3)
+        asm("ld.global.nc.L1::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(v.a), "=f"(v.b), "=f"(v.c), "=f"(v.d), "=f"(v.e), "=f"(v.f), "=f"(v.g), "=f"(v.h) : "l"(p));
+    else
+        v = ld8(p);
+    return v;
+}
+template <int H> __device__ __forceinline__ f4 ld4h(const void *p) {
+    f4 v;
+    if (H == 1)
+        asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else if (H == 2)
+        asm("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else if (H == 3)
+        asm("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else
+        v = ld4(p);
+    return v;
+}
+
 __device__ __forceinline__ bool link_is_leaf(int32_t link) { return link < 0 && link != kLinkDone && link != kLinkPop; }
 
 __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
@@ -212,7 +251,12 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
     bool leaf_l = false;  // the postponed leaf belongs to the light BVH
     float lsum = 0.0f;
     const int32_t scene_root = bvh.root4 == RT_LINK_NONE ? kLinkDone : bvh.root4;
+#if RT_EXT_SPLIT_NODES
+    const char *node_base = bvh.q4lo;
+    const size_t hi_off = bvh.q4_hi_off;
+#else
     const QNode4 *node_base = bvh.qnodes4;
+#endif
     uint32_t pool_next = 0, pool_end = 0;  // warp-uniform block of queue entries
     bool exhausted = false;                 // warp-uniform
 
@@ -257,7 +301,11 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                 lsum = 0.0f;
                 lmode = (__float_as_uint(d4.w) >> 31) != 0u && lbvh.root4 != RT_LINK_NONE;
                 ray |= __float_as_uint(d4.w) & 0x80000000u;
+#if RT_EXT_SPLIT_NODES
+                node_base = lmode ? lbvh.q4lo : bvh.q4lo;
+#else
                 node_base = lmode ? lbvh.qnodes4 : bvh.qnodes4;
+#endif
                 link = lmode ? lbvh.root4 : scene_root;  // a leaf root is postponed in the first step
             }
             pool_next += take;
@@ -299,7 +347,11 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                     }
                     if (need && !has && lmode) {
                         lmode = false;
+#if RT_EXT_SPLIT_NODES
+                        node_base = bvh.q4lo;
+#else
                         node_base = bvh.qnodes4;
+#endif
                         l = scene_root;
                     }
                     if (need) link = t < best_t ? l : kLinkPop;
@@ -315,8 +367,13 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                         }
                         ++sp;
                     };
+#if RT_EXT_SPLIT_NODES
+                    const char *np = node_base + static_cast<size_t>(static_cast<uint32_t>(link)) * 32u;
+                    const f8 na = ld8h<RT_EXT_NODE_L1>(np), nb = ld8h<RT_EXT_NODE_L1>(np + hi_off);  // grid, 6 plane words | 4 links
+#else
                     const char *np = reinterpret_cast<const char *>(node_base + link);
-                    const f8 na = ld8(np), nb = ld8(np + 32);  // 64 B node: grid, 6 plane words, 4 links
+                    const f8 na = ld8h<RT_EXT_NODE_L1>(np), nb = ld8h<RT_EXT_NODE_L1>(np + 32);  // 64 B node: grid, 6 plane words, 4 links
+#endif
                     const Node4Test nt = qnode4_test(f2u(na.a), f2u(na.b), f2u(na.c), f2u(na.d), f2u(na.e), f2u(na.f), f2u(na.g),
                                                      f2u(na.h), f2u(nb.a), idir, ood, one, eps, best_t);
                     float d0 = nt.d[0], d1 = nt.d[1], d2 = nt.d[2], d3 = nt.d[3];
@@ -391,8 +448,8 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                     };
                     // the second triangle is loaded speculatively (the array ends with a null triangle): the scene's
                     // leaves mostly hold a quad, and the load latency is paid once per leaf
-                    const f8 ta = ld8(p), tb = ld8(p + 64);
-                    const f4 ta2 = ld4(p + 32), tb2 = ld4(p + 96);
+                    const f8 ta = ld8h<RT_EXT_TRI_L1>(p), tb = ld8h<RT_EXT_TRI_L1>(p + 64);
+                    const f4 ta2 = ld4h<RT_EXT_TRI_L1>(p + 32), tb2 = ld4h<RT_EXT_TRI_L1>(p + 96);
                     bool last = tri(ta, ta2, k);
                     if (!last) last = tri(tb, tb2, k + 1);
                     more = !last;
@@ -416,6 +473,10 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
 #ifndef RT_SHADE_MINB
 #define RT_SHADE_MINB 0
 #endif
+#ifndef RT_SHADE_PREFETCH
+#define RT_SHADE_PREFETCH 1  // 0: off (38.25 ms per 256 spp); 1 (37.15): next iteration's queue records; 2: + its hit triangles / attributes; 3: + the radiance slot of a miss
+#endif
+__device__ __forceinline__ void pf_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #if RT_SHADE_MINB
 __global__ void __launch_bounds__(kShadeThreads, RT_SHADE_MINB) k_shade(
 #else
@@ -432,10 +493,24 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
     const bool last = bounce + 1 == s.ray_depth;
     const uint32_t lane = lane_id();
     uint32_t n_light = 0, n_shade = 0, n_ext = 0;
+#if RT_SHADE_PREFETCH
+    // Software pipeline of the work fetch: the cursor value of iteration k + 1 is requested during iteration k (its
+    // atomic is in flight while the warp shades) and turned, half an iteration ahead of their use, into L1 prefetches
+    // of the 32 queue records the warp will read next (and, level 2, into a look at their hit triangles, whose
+    // DTri / DAttr lines are prefetched at the end of the iteration).
+    uint32_t base_w = 0, ahead = 0;
+    if (lane == 0) base_w = atomicAdd(fetch_cursor, 32u);
+    base_w = __shfl_sync(FULL, base_w, 0);
+    if (lane == 0) ahead = atomicAdd(fetch_cursor, 32u);
+#endif
     for (;;) {
+#if RT_SHADE_PREFETCH
+        const uint32_t base = base_w;
+#else
         uint32_t base = 0;  // the warp pulls the next 32 queue entries
         if (lane == 0) base = atomicAdd(fetch_cursor, 32u);
         base = __shfl_sync(FULL, base, 0);
+#endif
         if (base >= count) break;
         const uint32_t i = base + lane;
         bool alive = false;
@@ -450,6 +525,9 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
             pixel = __float_as_uint(o4.w);
             sample = __float_as_uint(d4.w) & 0x7FFFFFFFu;
             bool live = true;
+#if RT_SHADE_PREFETCH >= 3
+            if (__float_as_int(h4.w) < 0) pf_l1(q.rad + ((__float_as_uint(d4.w) & 0x7FFFFFFFu) - bp.s0) * bp.npix + (__float_as_uint(o4.w) - bp.pix0));  // a miss adds the background
+#endif
             if (__float_as_uint(d4.w) >> 31) live = shade_resolve(s, thr, t4.w, q_load<1>(q.lpdf + i), thr);  // previous bounce
             if (live) {
                 ++n_ext;  // this extension ray's hit is consumed (cast_ray of the reference)
@@ -489,6 +567,26 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
                 }
             }
         }
+#if RT_SHADE_PREFETCH
+        // the next iteration's records -> L1; request the cursor value of the iteration after it
+        base_w = __shfl_sync(FULL, ahead, 0);
+        if (lane == 0) ahead = atomicAdd(fetch_cursor, 32u);
+        const uint32_t i_next = base_w + lane;
+#if RT_SHADE_PREFETCH >= 2
+        int32_t tri_next = -1;
+#endif
+        if (i_next < count) {
+            pf_l1(q.o_in + i_next);
+            pf_l1(q.d_in + i_next);
+            pf_l1(q.thr_in + i_next);
+#if RT_SHADE_PREFETCH >= 2
+            tri_next = __float_as_int(q.hit[i_next].w);
+#else
+            pf_l1(q.hit + i_next);
+#endif
+            if ((lane & 7u) == 0u) pf_l1(q.lpdf + i_next);
+        }
+#endif
         // warp-aggregated append: one atomicAdd per warp, slots handed out by __popc of the lower lanes
         const uint32_t mask = __ballot_sync(FULL, alive);
         uint32_t dst = 0;
@@ -499,6 +597,12 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
             q_store<2>(q.d_out + dst, make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u))));
             q_store<2>(q.thr_out + dst, make_float4(thr.x, thr.y, thr.z, pending));
         }
+#if RT_SHADE_PREFETCH >= 2
+        if (tri_next >= 0) {
+            pf_l1(s.scene.tris + tri_next);
+            pf_l1(s.attrs + tri_next);
+        }
+#endif
     }
     // block-level reduction of the work counters -> one atomic per CTA and counter
     __shared__ uint32_t s_cnt[3];
@@ -516,6 +620,16 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
     }
     __syncthreads();
     if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(q.stats + threadIdx.x, static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+}
+
+// QNode4 records -> the two 32-byte-stride arrays k_extend reads (DBvh::q4lo); one thread per 16-byte quarter
+__global__ void __launch_bounds__(256) k_split_nodes(const QNode4 *__restrict__ nodes, uint32_t n, char *__restrict__ lo, char *__restrict__ hi) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 4u) return;
+    const uint32_t node = t >> 2, quarter = t & 3u;
+    const uint4 v = reinterpret_cast<const uint4 *>(nodes)[t];
+    char *dst = (quarter < 2 ? lo : hi) + static_cast<size_t>(node) * 32u + (quarter & 1u) * 16u;
+    *reinterpret_cast<uint4 *>(dst) = v;
 }
 
 // accum[pixel] += sum_j sanitize(rad[j * npix + p])  — fixed order, deterministic, no atomics

@@ -122,6 +122,7 @@ struct DeviceState {
     // scene
     DevBuf<QNode4> qnodes4, lqnodes4;  // scene BVH and light BVH, 4-wide quantised (both traversed by k_extend)
     DevBuf<QNode8> qnodes8, lqnodes8;  // 8-wide (RT_EXT_WIDE8 builds)
+    DevBuf<uint4> q4split;             // both 4-wide node arrays once more, as two halves of 32-byte stride (DBvh::q4lo)
     DevBuf<DTri> tris, ltris, lsample;
     DevBuf<DAttr> attrs;
     DevBuf<DTangent> tangents;
@@ -435,6 +436,20 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
     d.scene.light.qnodes4 = d.lqnodes4.p;
     d.scene.scene.qnodes8 = d.qnodes8.p;
     d.scene.light.qnodes8 = d.lqnodes8.p;
+#if !RT_EXT_WIDE8
+    {   // the node halves k_extend reads: [scene lo | light lo | scene hi | light hi], 32 bytes per node and half
+        const size_t n_scene = device_built ? d.built_info[2] : p.scene.qnodes4.size(), n_light = p.light.qnodes4.size();
+        const size_t n_all = std::max<size_t>(n_scene + n_light, 1);
+        if (int rc = d.q4split.alloc(n_all * 4)) return rc;
+        char *lo = reinterpret_cast<char *>(d.q4split.p), *hi = lo + n_all * 32;
+        if (n_scene) rt::k_split_nodes<<<static_cast<uint32_t>((n_scene * 4 + 255) / 256), 256, 0, d.stream>>>(d.qnodes4.p, static_cast<uint32_t>(n_scene), lo, hi);
+        if (n_light) rt::k_split_nodes<<<static_cast<uint32_t>((n_light * 4 + 255) / 256), 256, 0, d.stream>>>(d.lqnodes4.p, static_cast<uint32_t>(n_light), lo + n_scene * 32, hi + n_scene * 32);
+        CU_CHECK(cudaGetLastError());
+        d.scene.scene.q4lo = lo;
+        d.scene.light.q4lo = lo + n_scene * 32;
+        d.scene.scene.q4_hi_off = d.scene.light.q4_hi_off = static_cast<uint32_t>(n_all * 32);
+    }
+#endif
     d.scene.scene.tris = d.tris.p;
     d.scene.light.nodes = nullptr;
     d.scene.light.qnodes = nullptr;
@@ -695,6 +710,9 @@ int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
         std::memset(d->h_stats, 0, 4 * sizeof(unsigned long long));
         CU_CHECK(cudaMallocHost(reinterpret_cast<void **>(&d->h_counters), sizeof(rtb::Counters)));
         int occ_e = 0, occ_s = 0;
+        // experiment knob: shared-memory carve-out of k_extend in percent of the maximum (the rest of the 256 KB is L1)
+        if (const char *e = std::getenv("RT_EXT_CARVEOUT"))
+            CU_CHECK(cudaFuncSetAttribute(RT_K_EXTEND, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(e)));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, RT_K_EXTEND, rt::kExtendThreads, 0));
         CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, rt::k_shade, rt::kShadeThreads, 0));
         // experiment knobs: resident CTAs per SM of the two persistent kernels (default: all that fit)
@@ -751,7 +769,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         if (!dp) continue;
         DeviceState &d = *dp;
         cudaSetDevice(d.device);
-        d.qnodes4.release(); d.lqnodes4.release(); d.qnodes8.release(); d.lqnodes8.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
+        d.qnodes4.release(); d.lqnodes4.release(); d.q4split.release(); d.qnodes8.release(); d.lqnodes8.release(); d.tprims.release(); d.tlights.release(); d.temit.release(); d.tris.release(); d.ltris.release(); d.lsample.release(); d.attrs.release();
         d.tangents.release(); d.light_extra.release(); d.materials.release(); d.textures.release();
         d.texels.release(); d.lut.release();
         d.arena.release(); d.means.release(); d.accum.release();

@@ -138,6 +138,13 @@ struct DBvh {
     const QNode *qnodes;   // quantised 2-wide nodes
     const QNode4 *qnodes4; // quantised 4-wide nodes (collapsed tree) and their root link
     int32_t root4;
+    // The same nodes as k_extend reads them (device only): bytes 0..31 of node i at q4lo + 32 i, bytes 32..63 at
+    // q4lo + q4_hi_off + 32 i.  With 64-byte records the first 256-bit load of a node step only ever touches the L1
+    // sector banks 0 and 2 and the second one banks 1 and 3; at a 32-byte stride each load spreads over all four,
+    // and a divergent warp's load costs fewer data-pipe wavefronts (tools/l1_probe.cu: -23 % when the nodes hit the
+    // L1, -10 % when they come from the L2).  The scene and the light BVH share one allocation and one q4_hi_off.
+    const char *q4lo;
+    uint32_t q4_hi_off;
     const QNode8 *qnodes8; // 8-wide nodes; node 0 is the root (n_nodes8 == 0: empty BVH)
     uint32_t n_nodes8;
     const DTri *tris;

@@ -5,6 +5,7 @@
 //   own256   2 x LDG.256 of the lane's own node (what k_extend does)
 //   pair256  2 x LDG.256, the two lanes of a pair fetch the two halves of ONE node per instruction (no exchange)
 //   pairx    pair256 + the 8 SHFL + 16 SEL that hand every lane its own node
+//   split256 2 x LDG.256, the two halves of a node in two arrays of 32-byte stride (all four sector banks per instruction)
 //   one256   1 x LDG.256 (a 32-byte node)
 //   own128   4 x LDG.128 of the lane's own node
 //   quad128  4 x LDG.128, four lanes fetch the four quarters of ONE node per instruction
@@ -70,6 +71,10 @@ template <int MODE> __global__ void __launch_bounds__(128) probe(const char *tab
                 SELX(a) SELX(b) SELX(c) SELX(d) SELX(e) SELX(f) SELX(g) SELX(h)
                 acc += sum8(k) - sum8(r);
             }
+        } else if (MODE == 8) {  // the two halves of a node in two separate arrays, 32-byte stride each
+            const char *pa = table + static_cast<size_t>(h_own) * 32;
+            const char *pb = table + (static_cast<size_t>(mask) + 1) * 32 + static_cast<size_t>(h_own) * 32;
+            acc += sum8(ld8(pa)) + sum8(ld8(pb));
         } else if (MODE == 3) {
             acc += sum8(ld8(table + static_cast<size_t>(h_own) * 32));
         } else if (MODE == 4) {
@@ -127,14 +132,26 @@ int main(int argc, char **argv) {
     cudaMalloc(&out, 4);
     const size_t sizes[3] = {size_t(32) << 10, size_t(32) << 20, size_t(1) << 30};
     const char *names[3] = {"32 KB table (L1-resident)", "32 MB table (L2-resident)", "1 GB table (HBM)"};
+    const int only_size = argc > 1 ? atoi(argv[1]) : -1, only_mode = argc > 2 ? atoi(argv[2]) : -1;  // for ncu: one pattern
     for (int s = 0; s < 3; ++s) {
+        if (only_size >= 0 && s != only_size) continue;
         char *table;
         cudaMalloc(&table, sizes[s]);
         cudaMemset(table, 0, sizes[s]);
         const uint32_t mask = static_cast<uint32_t>(sizes[s] / 64 - 1);
         printf("%s\n", names[s]);
+        if (only_mode >= 0) {
+            if (only_mode == 0) run<0>("own256", table, mask, 32, out, prop.multiProcessorCount, mhz);
+            if (only_mode == 8) run<8>("split256", table, mask, 32, out, prop.multiProcessorCount, mhz);
+            if (only_mode == 1) run<1>("pair256", table, mask, 32, out, prop.multiProcessorCount, mhz);
+            if (only_mode == 3) run<3>("one256", table, mask, 32, out, prop.multiProcessorCount, mhz);
+            if (only_mode == 4) run<4>("own128", table, mask, 32, out, prop.multiProcessorCount, mhz);
+            cudaFree(table);
+            continue;
+        }
         for (int active : {32, 20}) {
             run<0>("own256", table, mask, active, out, prop.multiProcessorCount, mhz);
+            run<8>("split256", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<1>("pair256", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<2>("pairx", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<3>("one256", table, mask, active, out, prop.multiProcessorCount, mhz);
