@@ -370,12 +370,19 @@ def run_gpu_arm(args, rank, world, local_rank):
         pst = rt.stats()
         rt.set_profiling(False)
         kernel_ms = {"generate": pst["kernel_ms"][0], "extend": pst["kernel_ms"][1], "shade": pst["kernel_ms"][2],
-                     "accumulate": pst["kernel_ms"][3], "render_total": pst["render_ms"]}
+                     "accumulate": pst["kernel_ms"][3], "lightpdf": pst["kernel_ms"][5], "render_total": pst["render_ms"]}
         peak = rt.fp32_peak_tflops()
         counts = reference_counts()
         flop_per_ray = FLOP_BOX * counts["box_tests_per_ray"] + FLOP_TRI * counts["tri_tests_per_ray"]
-        n_ext_launches = max(1, (pst["kernel_launches"] // (2 + 2 * scene.ray_depth)) * scene.ray_depth)
+        # launches of a batch: k_generate, depth x (k_extend + k_shade), k_accumulate and, with lights, k_lightpdf_list for
+        # every queue but the camera rays'
+        has_lights = len(scene.light_bvh.objects) > 0
+        per_batch = 2 + 2 * scene.ray_depth + (max(scene.ray_depth - 1, 0) if has_lights else 0)
+        n_ext_launches = max(1, (pst["kernel_launches"] // per_batch) * scene.ray_depth)
         achieved = flop_per_ray * pst["extension_rays"] / (pst["kernel_ms"][1] * 1e-3) / 1e12
+        # the light-pdf traversals were a mode of k_extend until round 2 (no algorithmic flop credited, their time in
+        # the denominator); they now run in k_lightpdf_list: the figure with its time added back, for comparison
+        ext_plus_light_ms = pst["kernel_ms"][1] + pst["kernel_ms"][5]
         traffic = traffic_note = None
         try:  # DRAM bytes per extension ray of k_extend from the committed `ncu --set full` capture
             with open(os.path.join(ROOT, "profiles", "k_extend_dram.json")) as f:
@@ -391,7 +398,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "algorithmic_flop_per_ray": flop_per_ray, "rays_per_launch": pst["extension_rays"] / n_ext_launches,
                 "avg_launch_ms": pst["kernel_ms"][1] / n_ext_launches, "launches": n_ext_launches,
                 "extend_share_of_step": pst["kernel_ms"][1] / max(pst["render_ms"], 1e-9),
-                "mrays_per_s_in_kernel": pst["extension_rays"] / (pst["kernel_ms"][1] * 1e-3) / 1e6}
+                "mrays_per_s_in_kernel": pst["extension_rays"] / (pst["kernel_ms"][1] * 1e-3) / 1e6,
+                "frac_with_lightpdf_kernel_time": (flop_per_ray * pst["extension_rays"] / (ext_plus_light_ms * 1e-3) / 1e12 / peak) if peak else None}
         if world == 1:
             cpu = cpu_throughput(args.cpu_budget)
 

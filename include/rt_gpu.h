@@ -174,7 +174,7 @@ typedef struct rt_stats {
     uint64_t shades;           /* shade() evaluations incl. alpha pass-throughs */
     double render_ms;          /* device time of rt_gpu_render (CUDA events), max over devices */
     double reduce_ms;          /* device time of the multi-device reduce (0 for one device) */
-    double kernel_ms[8];       /* per-kernel device time: 0 generate 1 extend 2 shade 3 accumulate 4 ids; filled only with RT_PROFILE_KERNELS */
+    double kernel_ms[8];       /* per-kernel device time: 0 generate 1 extend 2 shade 3 accumulate 4 ids 5 light pdf; filled only with RT_PROFILE_KERNELS */
     uint64_t kernel_launches;  /* kernels launched by the last rt_gpu_render */
 } rt_stats;
 

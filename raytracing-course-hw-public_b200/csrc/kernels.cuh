@@ -57,6 +57,8 @@ struct Queues {
     uint32_t *fetch_shade;  // [ray_depth] work-fetch cursors of k_shade
     unsigned long long *stats;  // [4] extension rays, light pdf rays, shades, samples
     float *lpdf;                // light pdf of the queued ray (bvh_mix_dist::pdf), written by k_extend for pending paths
+    uint32_t *light_list;       // RT_LIGHT_KERNEL == 2: indices (in the OUT queue) of the pending rays that pass the light box
+    uint32_t *light_count;      // [ray_depth + 1] sizes of that list, per queue
 };
 
 // Queue records are read once and written once per bounce (streaming), the scene is re-read by every ray: with
@@ -114,6 +116,15 @@ __global__ void __launch_bounds__(256) k_generate(Camera cam, BatchParams bp, Qu
     q_store<2>(q.d_out + slot, make_float4(dir.x, dir.y, dir.z, __uint_as_float(sample)));
     q_store<2>(q.thr_out + slot, make_float4(1.0f, 1.0f, 1.0f, -1.0f));
     q_store<3>(q.rad + slot, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+}
+
+// one term of bvh_mix_dist::pdf: the light triangle `le` (normal, area) hit at distance t along d
+// (raytracer.h:79-84,255-261: every hit counts, occluded or not, both faces); the 1 / n_lights is applied to the sum
+__device__ __forceinline__ float light_pdf_term(f3 d, float t, f4 le) {
+    const f3 xy = d * t;  // y - x
+    const float d2 = len2(xy);
+    const f3 w = xy * rsqrtf(d2);
+    return __fdividef(d2, fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);  // MUFU.RCP: 2e-7 of a pdf term
 }
 
 // ---- k_extend -----------------------------------------------------------------------------------------
@@ -181,6 +192,16 @@ __device__ __forceinline__ float rcp_rn(float x) {
 #ifndef RT_EXT_TRI_L1
 #define RT_EXT_TRI_L1 1  // no_allocate: k_extend 159.5 -> 157.3 ms per 256 spp (evict_first: no change; evict_last on the nodes: +1 %)
 #endif
+// bvh_mix_dist::pdf of the pending rays: 0 = a traversal mode of k_extend (rounds 1 / 2, and the 8-wide build);
+// 2 = k_shade tests the ray it queues against the box of all lights and lists those that pass, k_lightpdf_list
+// traverses the light BVH for them (1, a light kernel that scanned the whole queue, was measured and removed)
+#ifndef RT_LIGHT_KERNEL
+#define RT_LIGHT_KERNEL 2
+#endif
+#if defined(RT_EXT_WIDE8) && RT_EXT_WIDE8
+#undef RT_LIGHT_KERNEL
+#define RT_LIGHT_KERNEL 0
+#endif
 #ifndef RT_EXT_SPLIT_NODES
 #define RT_EXT_SPLIT_NODES 1  // node halves from two arrays of 32-byte stride (DBvh::q4lo) instead of 64-byte records
 #endif
@@ -247,9 +268,13 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1), idir = mk3(0, 0, 1), ood = mk3(0, 0, 0);
     float best_t = INFINITY, best_b = 0.0f, best_c = 0.0f;
     int32_t best_tri = -1;
+#if RT_LIGHT_KERNEL
+    constexpr bool leaf_l = false;  // the light BVH is traversed by k_lightpdf
+#else
     bool lmode = false;   // the lane is in the light BVH
     bool leaf_l = false;  // the postponed leaf belongs to the light BVH
     float lsum = 0.0f;
+#endif
     const int32_t scene_root = bvh.root4 == RT_LINK_NONE ? kLinkDone : bvh.root4;
 #if RT_EXT_SPLIT_NODES
     const char *node_base = bvh.q4lo;
@@ -265,7 +290,9 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
         const bool idle = link == kLinkDone && leaf == 0;
         if (idle && ray != kNoRay) {
             const uint32_t r = ray & 0x7FFFFFFFu;
+#if !RT_LIGHT_KERNEL
             if (ray >> 31) q_store<0>(q.lpdf + r, lsum * inv_n_lights);  // 0 when the scene has no light BVH
+#endif
             q_store<0>(q.hit + r, make_float4(best_t, best_b, best_c, __int_as_float(best_tri)));
             ray = kNoRay;
         }
@@ -298,6 +325,9 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                 best_tri = -1;
                 sp = 0;
                 top = s_stack + threadIdx.x;
+#if RT_LIGHT_KERNEL
+                link = scene_root;  // a leaf root is postponed in the first step
+#else
                 lsum = 0.0f;
                 lmode = (__float_as_uint(d4.w) >> 31) != 0u && lbvh.root4 != RT_LINK_NONE;
                 ray |= __float_as_uint(d4.w) & 0x80000000u;
@@ -307,6 +337,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                 node_base = lmode ? lbvh.qnodes4 : bvh.qnodes4;
 #endif
                 link = lmode ? lbvh.root4 : scene_root;  // a leaf root is postponed in the first step
+#endif
             }
             pool_next += take;
             if (avail == 0 && m_idle == FULL) break;  // queue drained and nothing in flight
@@ -345,6 +376,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                             t = e.y;
                         }
                     }
+#if !RT_LIGHT_KERNEL
                     if (need && !has && lmode) {
                         lmode = false;
 #if RT_EXT_SPLIT_NODES
@@ -354,6 +386,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
 #endif
                         l = scene_root;
                     }
+#endif
                     if (need) link = t < best_t ? l : kLinkPop;
                 }
                 // (2) at most one node step: four slab tests, nearest child next, the others onto the stack
@@ -407,7 +440,9 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                 //     one waits with it
                 if (leaf == 0 && link_is_leaf(link)) {
                     leaf = link;
+#if !RT_LIGHT_KERNEL
                     leaf_l = lmode;
+#endif
                     link = kLinkPop;
                 }
             }
@@ -431,13 +466,12 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
                         const float inv = rcp_rn(-dot(d, n));
                         const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
                         if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < best_t) {
+#if !RT_LIGHT_KERNEL
                             if (lt) {  // every hit counts, occluded or not, both faces (raytracer.h:79-84,255-261)
-                                const f4 le = ld4(light_extra + kk);
-                                const f3 xy = d * t;  // y - x
-                                const float d2 = len2(xy);
-                                const f3 w = xy * rsqrtf(d2);
-                                lsum += __fdividef(d2, fabsf(dot(w, mk3(le.x, le.y, le.z))) * le.w);  // MUFU.RCP: 2e-7 of a pdf term
-                            } else {
+                                lsum += light_pdf_term(d, t, ld4(light_extra + kk));
+                            } else
+#endif
+                            {
                                 best_t = t;
                                 best_b = beta;
                                 best_c = gamma;
@@ -461,6 +495,118 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
     }
 }
 
+// ---- k_lightpdf_list ----------------------------------------------------------------------------------
+// bvh_mix_dist::pdf (raytracer.h:363-375) of the pending rays: an all-hit traversal of the light BVH (nothing is culled,
+// the visiting order does not matter), result in q.lpdf.  As a traversal mode of k_extend (rounds 1 / 2) it cost 10.4 %
+// of that kernel (16.3 of 156 ms per 256 spp): the few node steps of a light query went through the sorted,
+// stack-based, leaf-postponing machinery of the closest-hit search, and cost k_extend three registers.  Now
+//   * k_shade, when it queues a pending ray, tests it against the box of all lights (six planes): a miss gets
+//     lpdf = 0 there and then, the others (33-50 % on config 4: every light-sampled direction passes) are listed
+//     with a warp-aggregated append;
+//   * k_lightpdf_list traverses the light BVH for the listed rays only, one thread per ray, unordered, with a stack of
+//     links.
+// Measured on config 4 per 256 spp: k_extend 156.1 -> 137.7 ms, k_lightpdf_list 6.0 ms, k_shade +1.7 ms.  A variant that
+// scanned the whole queue in the light kernel (box test + CTA-level compaction there) took 11.2 ms: the scan is bound
+// by the latency of its own record loads.
+struct LightBox {
+    float lo[3], hi[3];  // box of all light triangles with a margin (rt_gpu.cu, upload)
+};
+constexpr int kLightThreads = 256;
+
+__device__ __forceinline__ float light_traverse(const DBvh &lbvh, const DLight *__restrict__ light_extra, f3 o, f3 d, f3 idir, f3 ood,
+                                                float eps, uint32_t one) {
+    int32_t stack[RT_EXT_STACK_CAP];  // the upload bounds the need of an unordered traversal as well (stack_need4)
+    int sp = 0;
+    float lsum = 0.0f;
+    int32_t link = lbvh.root4;
+    for (;;) {
+        if (link >= 0) {
+            const char *np = reinterpret_cast<const char *>(lbvh.qnodes4 + link);
+            const f8 na = ld8(np), nb = ld8(np + 32);
+            const Node4Test nt = qnode4_test(f2u(na.a), f2u(na.b), f2u(na.c), f2u(na.d), f2u(na.e), f2u(na.f), f2u(na.g), f2u(na.h),
+                                             f2u(nb.a), idir, ood, one, eps, INFINITY);
+            const int32_t l[4] = {static_cast<int32_t>(f2u(nb.b)), static_cast<int32_t>(f2u(nb.c)), static_cast<int32_t>(f2u(nb.d)),
+                                  static_cast<int32_t>(f2u(nb.e))};
+            link = kLinkPop;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (nt.d[c] < INFINITY) {
+                    if (link == kLinkPop) link = l[c];
+                    else stack[sp++] = l[c];
+                }
+            }
+        } else if (link != kLinkPop) {  // leaf: intersect_ray_triangle (bvh.h:36-65) on every triangle, every hit counts
+            uint32_t k = static_cast<uint32_t>(~link);
+            for (;;) {
+                const char *p = reinterpret_cast<const char *>(lbvh.tris + k);
+                const f8 ta = ld8(p);
+                const f4 t2 = ld4(p + 32);
+                const f3 e1 = mk3(ta.e, ta.f, ta.g), e2 = mk3(t2.x, t2.y, t2.z);
+                const f3 n = cross(e1, e2);
+                const f3 y = o - mk3(ta.a, ta.b, ta.c);
+                const f3 r = cross(d, y);
+                const float inv = rcp_rn(-dot(d, n));
+                const float beta = -dot(e2, r) * inv, gamma = dot(e1, r) * inv, t = dot(y, n) * inv;
+                if (beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f && t >= eps && t < INFINITY)
+                    lsum += light_pdf_term(d, t, ld4(light_extra + k));
+                if (f2u(ta.d) & RT_LAST_BIT) break;
+                ++k;
+            }
+            link = kLinkPop;
+        }
+        if (link == kLinkPop) {
+            if (sp == 0) break;
+            link = stack[--sp];
+        }
+    }
+    return lsum;
+}
+
+// RT_LIGHT_KERNEL == 2: only the rays k_shade listed (those that pass the box of all lights).  The list index and the
+// ray record of the next iteration are requested before the current ray is traversed (two dependent gathers from DRAM
+// per ray: without the pipeline the kernel ran at a third of its instruction rate).
+__global__ void __launch_bounds__(kLightThreads) k_lightpdf_list(DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps,
+                                                                Queues q, uint32_t bounce, uint32_t one) {
+    const uint32_t n = q.light_count[bounce * kCounterStride];
+    const uint32_t stride = gridDim.x * kLightThreads;
+    uint32_t j = blockIdx.x * kLightThreads + threadIdx.x;
+    if (j >= n) return;
+    uint32_t i_cur = __ldcs(q.light_list + j);
+    uint32_t i_nxt = j + stride < n ? __ldcs(q.light_list + j + stride) : 0u;
+    float4 d4 = q.d_in[i_cur], o4 = q.o_in[i_cur];
+    for (;;) {
+        const bool more = j + stride < n;
+        float4 d4n = d4, o4n = o4;
+        uint32_t i_nn = 0u;
+        if (more) {
+            d4n = q.d_in[i_nxt];
+            o4n = q.o_in[i_nxt];
+            if (j + 2u * stride < n) i_nn = __ldcs(q.light_list + j + 2u * stride);
+        }
+        const f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
+        const f3 idir = mk3(rcp_rn(d.x), rcp_rn(d.y), rcp_rn(d.z));
+        const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        q_store<0>(q.lpdf + i_cur, light_traverse(lbvh, light_extra, o, d, idir, ood, eps, one) * inv_n_lights);
+        if (!more) break;
+        j += stride;
+        i_cur = i_nxt;
+        i_nxt = i_nn;
+        d4 = d4n;
+        o4 = o4n;
+    }
+}
+
+// slab test of a ray against the box of all lights; NaNs (0 * inf) drop out of fminf / fmaxf: conservative
+__device__ __forceinline__ bool light_box_test(const LightBox &box, f3 o, f3 d, float eps) {
+    const float ix = rcp_rn(d.x), iy = rcp_rn(d.y), iz = rcp_rn(d.z);
+    const float ax = (box.lo[0] - o.x) * ix, bx = (box.hi[0] - o.x) * ix;
+    const float ay = (box.lo[1] - o.y) * iy, by = (box.hi[1] - o.y) * iy;
+    const float az = (box.lo[2] - o.z) * iz, bz = (box.hi[2] - o.z) * iz;
+    const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), eps));
+    const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return t0 <= t1;
+}
+
 // k_shade, bounce b.  For every entry of queue b:
 //   1. if the path is pending (its previous bounce sampled a direction and the scene has lights): resolve that
 //      bounce with the light pdf k_extend summed along this very ray — p = p_partial + (1 - VNDF_factor)/2 * lpdf,
@@ -482,7 +628,7 @@ __global__ void __launch_bounds__(kShadeThreads, RT_SHADE_MINB) k_shade(
 #else
 __global__ void __launch_bounds__(kShadeThreads) k_shade(
 #endif
-    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q, uint32_t bounce) {
+    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q, uint32_t bounce, LightBox light_box) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
@@ -590,8 +736,25 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
         // warp-aggregated append: one atomicAdd per warp, slots handed out by __popc of the lower lanes
         const uint32_t mask = __ballot_sync(FULL, alive);
         uint32_t dst = 0;
+#if RT_LIGHT_KERNEL == 2
+        // a pending ray that misses the box of all lights has light pdf 0; the others are listed for k_lightpdf_list
+        // (both atomics are issued before either result is waited for)
+        const bool pend = alive && pending >= 0.0f;
+        const bool pass = pend && light_box_test(light_box, o, d, s.eps);
+        const uint32_t mp = __ballot_sync(FULL, pass);
+        uint32_t lp = 0;
+        if (lane == 0) {
+            if (mask) dst = atomicAdd(out_counter, static_cast<uint32_t>(__popc(mask)));
+            if (mp) lp = atomicAdd(q.light_count + (bounce + 1) * kCounterStride, static_cast<uint32_t>(__popc(mp)));
+        }
+        dst = __shfl_sync(FULL, dst, 0) + static_cast<uint32_t>(__popc(mask & ((1u << lane) - 1u)));
+        lp = __shfl_sync(FULL, lp, 0) + static_cast<uint32_t>(__popc(mp & ((1u << lane) - 1u)));
+        if (pend && !pass) q_store<0>(q.lpdf + dst, 0.0f);
+        if (pass) q.light_list[lp] = dst;
+#else
         if (lane == 0 && mask) dst = atomicAdd(out_counter, static_cast<uint32_t>(__popc(mask)));
         dst = __shfl_sync(FULL, dst, 0) + static_cast<uint32_t>(__popc(mask & ((1u << lane) - 1u)));
+#endif
         if (alive) {
             q_store<2>(q.o_out + dst, make_float4(o.x, o.y, o.z, __uint_as_float(pixel)));
             q_store<2>(q.d_out + dst, make_float4(d.x, d.y, d.z, __uint_as_float(sample | (pending >= 0.0f ? 0x80000000u : 0u))));

@@ -108,9 +108,9 @@ template <class T> struct DevBuf {
     }
 };
 
-constexpr size_t kBytesPerPath = 8 * sizeof(float4) + sizeof(float);  // q_o, q_d, q_thr (x2 parities) + hit + rad + lpdf
+constexpr size_t kBytesPerPath = 8 * sizeof(float4) + 2 * sizeof(float);  // q_o, q_d, q_thr (x2 parities) + hit + rad + lpdf + light list
 
-enum KernelKind { K_GENERATE = 0, K_EXTEND = 1, K_SHADE = 2, K_ACCUMULATE = 3, K_IDS = 4, K_COUNT = 8 };
+enum KernelKind { K_GENERATE = 0, K_EXTEND = 1, K_SHADE = 2, K_ACCUMULATE = 3, K_IDS = 4, K_LIGHTPDF = 5, K_COUNT = 8 };
 
 struct DeviceState {
     int device = 0;
@@ -153,6 +153,7 @@ struct DeviceState {
     size_t queue_cap = 0;  // paths the arena holds
     float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr}, *qthr[2] = {nullptr, nullptr}, *hit = nullptr, *rad = nullptr;
     float *lpdf = nullptr;
+    uint32_t *light_list = nullptr;  // RT_LIGHT_KERNEL == 2: queue indices of the pending rays that pass the light box
     DevBuf<float4> accum;
     DevBuf<float> means;   // packed rgb means (rt_gpu_readback)
     DevBuf<uint32_t> counters;
@@ -168,11 +169,11 @@ struct DeviceState {
         const size_t b16 = up(cap * sizeof(float4)), b4 = up(cap * sizeof(float));
         arena.release();
         queue_cap = 0;
-        if (int rc = arena.alloc(8 * b16 + b4)) return rc;
+        if (int rc = arena.alloc(8 * b16 + 2 * b4)) return rc;
         uint8_t *p = arena.p;
         if (std::getenv("RT_TIMING"))
             std::fprintf(stderr, "rt_gpu: queue arena %p, %.1f MiB, base mod 512 MiB = %zu MiB\n", static_cast<void *>(p),
-                         (8 * b16 + b4) / 1048576.0, (reinterpret_cast<size_t>(p) >> 20) & 511);
+                         (8 * b16 + 2 * b4) / 1048576.0, (reinterpret_cast<size_t>(p) >> 20) & 511);
         auto take = [&](size_t b) { uint8_t *r = p; p += b; return r; };
         for (int i = 0; i < 2; ++i) {
             qo[i] = reinterpret_cast<float4 *>(take(b16));
@@ -182,13 +183,15 @@ struct DeviceState {
         hit = reinterpret_cast<float4 *>(take(b16));
         rad = reinterpret_cast<float4 *>(take(b16));
         lpdf = reinterpret_cast<float *>(take(b4));
+        light_list = reinterpret_cast<uint32_t *>(take(b4));
         queue_cap = cap;
         return RT_OK;
     }
     DevBuf<unsigned long long> stats;
     DevBuf<int32_t> prim_ids;
     DevBuf<uint8_t> rgb8;
-    int extend_blocks = 0, shade_blocks = 0;
+    int extend_blocks = 0, shade_blocks = 0, light_blocks = 0;
+    rt::LightBox light_box{};  // box of all light triangles (k_shade tests the rays it queues against it)
     // profiling
     std::vector<std::pair<cudaEvent_t, int>> marks;  // event recorded AFTER a kernel of that kind
     std::vector<cudaEvent_t> event_pool;
@@ -421,6 +424,25 @@ int upload_to_device(DeviceState &d, const rt_scene_desc &sc, const rt::PackedSc
         if (int rc = d.tangents.upload(p.tangents, d.stream)) return rc;
         std::memset(d.built_info, 0, sizeof d.built_info);
     }
+    {   // box of all light triangles, widened by 1e-4 of its size and of the coordinates' magnitude: a ray that misses
+        // it has no light-pdf term (k_lightpdf); the last entry of light.tris is the null triangle
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        const size_t n_lt = p.light.tris.empty() ? 0 : p.light.tris.size() - 1;
+        for (size_t k = 0; k < n_lt; ++k) {
+            const DTri &t = p.light.tris[k];
+            const float v[3][3] = {{t.ax, t.ay, t.az}, {t.ax + t.e1x, t.ay + t.e1y, t.az + t.e1z}, {t.ax + t.e2x, t.ay + t.e2y, t.az + t.e2z}};
+            for (int j = 0; j < 3; ++j)
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = std::min(lo[a], v[j][a]);
+                    hi[a] = std::max(hi[a], v[j][a]);
+                }
+        }
+        for (int a = 0; a < 3; ++a) {
+            const float m = n_lt ? 1e-4f * std::max({hi[a] - lo[a], std::fabs(lo[a]), std::fabs(hi[a]), 1e-3f}) : 0.0f;
+            d.light_box.lo[a] = lo[a] - m;
+            d.light_box.hi[a] = hi[a] + m;
+        }
+    }
     if (int rc = d.ltris.upload(p.light.tris, d.stream)) return rc;
     if (int rc = d.lsample.upload(p.light_sample, d.stream)) return rc;
     if (int rc = d.light_extra.upload(p.light_extra, d.stream)) return rc;
@@ -599,7 +621,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
     const size_t cap = std::min(max_paths, want_total);
     if (int rc = d.alloc_queues(cap)) return rc;
     const uint32_t qdepth = std::max(depth, 1u);
-    const size_t n_counters = (3 * static_cast<size_t>(qdepth) + 1) * rt::kCounterStride;  // one 256-byte line each
+    const size_t n_counters = (4 * static_cast<size_t>(qdepth) + 2) * rt::kCounterStride;  // one 256-byte line each
     if (int rc = d.counters.alloc(n_counters)) return rc;
 
     // Queues of bounce b: in = parity b & 1, out = the other one (k_generate fills queue 0 through `out` of b = -1)
@@ -619,6 +641,8 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
         q.fetch_shade = d.counters.p + (2 * qdepth + 1) * rt::kCounterStride;
         q.stats = d.stats.p;
         q.lpdf = d.lpdf;
+        q.light_list = d.light_list;
+        q.light_count = d.counters.p + (3 * qdepth + 1) * rt::kCounterStride;
         return q;
     };
     const rt::Queues q_gen = queues_of(-1);
@@ -655,9 +679,16 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
             }
             for (uint32_t b = 0; b < depth; ++b) {
                 const rt::Queues q = queues_of(static_cast<int>(b));
+#if RT_LIGHT_KERNEL
+                if (b > 0 && d.scene.n_lights > 0) {  // queue 0 holds camera rays: nothing is pending
+                    rt::k_lightpdf_list<<<d.light_blocks, rt::kLightThreads, 0, d.stream>>>(d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b, 0x3F800000u);
+                    mark(ctx, d, K_LIGHTPDF);
+                    ++launches;
+                }
+#endif
                 RT_K_EXTEND<<<d.extend_blocks, rt::kExtendThreads, 0, d.stream>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q, b, 0x3F800000u);
                 mark(ctx, d, K_EXTEND);
-                rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b);
+                rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, d.stream>>>(d.scene, d.lut.p, bp, q, b, d.light_box);
                 mark(ctx, d, K_SHADE);
             }
             rt::k_accumulate<<<(bp.npix + 255) / 256, 256, 0, d.stream>>>(bp, d.rad, d.accum.p);
@@ -718,6 +749,9 @@ int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
         // experiment knobs: resident CTAs per SM of the two persistent kernels (default: all that fit)
         if (const char *e = std::getenv("RT_EXT_CTAS_PER_SM")) occ_e = std::min(occ_e, std::max(1, std::atoi(e)));
         if (const char *e = std::getenv("RT_SHADE_CTAS_PER_SM")) occ_s = std::min(occ_s, std::max(1, std::atoi(e)));
+        int occ_l = 0;
+        CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, rt::k_lightpdf_list, rt::kLightThreads, 0));
+        d->light_blocks = d->sm_count * std::max(occ_l, 1);
         d->extend_blocks = d->sm_count * std::max(occ_e, 1);
         d->shade_blocks = d->sm_count * std::max(occ_s, 1);
     }
@@ -999,6 +1033,15 @@ int rt_gpu_render(rt_gpu_ctx *ctx, const rt_render_params *params) {
         st.light_pdf_rays += hs[1];
         st.shades += hs[2];
         st.samples += hs[3];
+        if (ctx->profiling && std::getenv("RT_TIMING") && d.counters.p) {  // queue and light-list sizes of the last batch
+            std::vector<uint32_t> hc(d.counters.n);
+            cudaMemcpy(hc.data(), d.counters.p, d.counters.n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            const uint32_t qd = std::max(d.scene.ray_depth, 1u);
+            std::string line = "rt_gpu queue sizes (last batch), bounce: rays / listed for k_lightpdf:";
+            for (uint32_t b = 0; b <= qd && (3 * qd + 1 + b) * rt::kCounterStride < hc.size(); ++b)
+                line += " " + std::to_string(hc[b * rt::kCounterStride]) + "/" + std::to_string(hc[(3 * qd + 1 + b) * rt::kCounterStride]);
+            std::fprintf(stderr, "%s\n", line.c_str());
+        }
         if (ctx->profiling) {
             double per_kind[K_COUNT] = {0};
             for (size_t i = 1; i < d.marks.size(); ++i) {

@@ -11,7 +11,7 @@ for spec in "$@"; do
 import json
 try:
     d=json.load(open("gpurun_out/ab_${tag}.json")); k=d["kernel_ms_profiled_step"]
-    print("$spec value=%.1f extend=%.2f shade=%.2f total=%.2f frac=%.4f"%(d["value"],k["extend"],k["shade"],k["render_total"],d["roofline"]["frac"]))
+    print("$spec value=%.1f extend=%.2f light=%.2f shade=%.2f total=%.2f frac=%.4f"%(d["value"],k["extend"],k.get("lightpdf",0),k["shade"],k["render_total"],d["roofline"]["frac"]))
 except Exception as e:
     print("$spec failed", e)
 PY
