@@ -665,6 +665,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
             bp.npix = npix;
             bp.s0 = s0;
             bp.k = std::min(k_max, s_end - s0);
+            bp.tiled = !ids_mode && pix0 == 0 && npix == n_pix && W % 8 == 0 && H % 4 == 0 && !std::getenv("RT_NO_TILES");
             const uint32_t n = bp.npix * bp.k;
             CU_CHECK(cudaMemsetAsync(d.counters.p, 0, n_counters * sizeof(uint32_t), d.stream));
             rt::k_generate<<<(n + 255) / 256, 256, 0, d.stream>>>(cam, bp, q_gen);
