@@ -202,6 +202,38 @@ def test_determinism_and_sample_split(rt, golden_scene):
     assert not np.array_equal(other, full)
 
 
+def test_queue_order_and_light_list_do_not_change_the_image(rt, golden_scene):
+    """Round-2 scheduling changes that must not move a bit: (1) camera rays are queued in 8 x 4 pixel tiles when the
+    image allows it (RT_NO_TILES=1 switches back to row-major; a path's radiance slot follows from its pixel and
+    sample, not from its queue position); (2) the light pdf of a pending ray comes from k_lightpdf_list for the rays
+    inside the box of all lights and is 0 for the others, so a render with lights launches one more kernel per bounce
+    after the first."""
+    sc = golden_scene("small_lights")
+    rt.upload_scene(sc)
+    w, h, s = 96, 64, 6  # tiled: 96 % 8 == 0 and 64 % 4 == 0
+    rt.render(w, h, s, seed=11)
+    tiled, st = rt.readback()
+    os.environ["RT_NO_TILES"] = "1"
+    try:
+        rt.render(w, h, s, seed=11)
+        linear, st2 = rt.readback()
+    finally:
+        del os.environ["RT_NO_TILES"]
+    assert np.array_equal(tiled, linear)
+    assert st["extension_rays"] == st2["extension_rays"] and st["light_pdf_rays"] == st2["light_pdf_rays"]
+    if not os.environ.get("RT_GPU_LIB"):  # (an alternative build, e.g. the 8-wide one, keeps the light traversal in k_extend)
+        depth = sc.ray_depth
+        assert len(sc.light_bvh.objects) > 0
+        # one batch: k_generate, depth x (k_extend + k_shade), k_accumulate, k_lightpdf_list for queues 1 .. depth - 1
+        assert st["kernel_launches"] == 2 + 2 * depth + (depth - 1)
+        sc2 = golden_scene("tiny")
+        rt.upload_scene(sc2)
+        rt.render(40, 32, 2, seed=1)
+        _, st3 = rt.readback()
+        lights = len(sc2.light_bvh.objects) > 0
+        assert st3["kernel_launches"] == 2 + 2 * sc2.ray_depth + ((sc2.ray_depth - 1) if lights else 0)
+
+
 def test_pixel_range_renders_add_up(rt, golden_scene):
     """Image-tile split: disjoint pixel ranges rendered separately (accumulating) give the full image bit for bit,
     and a range leaves the other pixels untouched."""

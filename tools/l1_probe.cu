@@ -6,6 +6,7 @@
 //   pair256  2 x LDG.256, the two lanes of a pair fetch the two halves of ONE node per instruction (no exchange)
 //   pairx    pair256 + the 8 SHFL + 16 SEL that hand every lane its own node
 //   split256 2 x LDG.256, the two halves of a node in two arrays of 32-byte stride (all four sector banks per instruction)
+//   split256na  the same with L1::no_allocate
 //   one256   1 x LDG.256 (a 32-byte node)
 //   own128   4 x LDG.128 of the lane's own node
 //   quad128  4 x LDG.128, four lanes fetch the four quarters of ONE node per instruction
@@ -24,6 +25,13 @@ struct f8 {
 __device__ __forceinline__ f8 ld8(const void *p) {
     f8 v;
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.a), "=f"(v.b), "=f"(v.c), "=f"(v.d), "=f"(v.e), "=f"(v.f), "=f"(v.g), "=f"(v.h)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ f8 ld8na(const void *p) {  // L1::no_allocate
+    f8 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v.a), "=f"(v.b), "=f"(v.c), "=f"(v.d), "=f"(v.e), "=f"(v.f), "=f"(v.g), "=f"(v.h)
                  : "l"(p));
     return v;
@@ -75,6 +83,10 @@ template <int MODE> __global__ void __launch_bounds__(128) probe(const char *tab
             const char *pa = table + static_cast<size_t>(h_own) * 32;
             const char *pb = table + (static_cast<size_t>(mask) + 1) * 32 + static_cast<size_t>(h_own) * 32;
             acc += sum8(ld8(pa)) + sum8(ld8(pb));
+        } else if (MODE == 9) {  // split256 with L1::no_allocate
+            const char *pa = table + static_cast<size_t>(h_own) * 32;
+            const char *pb = table + (static_cast<size_t>(mask) + 1) * 32 + static_cast<size_t>(h_own) * 32;
+            acc += sum8(ld8na(pa)) + sum8(ld8na(pb));
         } else if (MODE == 3) {
             acc += sum8(ld8(table + static_cast<size_t>(h_own) * 32));
         } else if (MODE == 4) {
@@ -152,6 +164,7 @@ int main(int argc, char **argv) {
         for (int active : {32, 20}) {
             run<0>("own256", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<8>("split256", table, mask, active, out, prop.multiProcessorCount, mhz);
+            run<9>("split256na", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<1>("pair256", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<2>("pairx", table, mask, active, out, prop.multiProcessorCount, mhz);
             run<3>("one256", table, mask, active, out, prop.multiProcessorCount, mhz);

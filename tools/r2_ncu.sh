@@ -20,5 +20,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_extend -s 1 -c
 echo "ncu extend rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 1 -c 2 -f -o gpurun_out/${TAG}_shade $CMD2 > gpurun_out/${TAG}_ncu_shade.log 2>&1
 echo "ncu shade rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:k_lightpdf -s 0 -c 2 -f -o gpurun_out/${TAG}_lightpdf $CMD2 > gpurun_out/${TAG}_ncu_lightpdf.log 2>&1
+echo "ncu lightpdf rc=$?"
 ls -la gpurun_out/${TAG}*
 exit 0
