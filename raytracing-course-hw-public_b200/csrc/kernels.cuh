@@ -57,7 +57,10 @@ struct Queues {
     uint32_t *fetch_ext;    // [ray_depth] work-fetch cursors of k_extend
     uint32_t *fetch_shade;  // [ray_depth] work-fetch cursors of k_shade
     unsigned long long *stats;  // [4] extension rays, light pdf rays, shades, samples
-    float *lpdf;                // light pdf of the queued ray (bvh_mix_dist::pdf), written by k_extend for pending paths
+    float *lpdf;                // light pdf (bvh_mix_dist::pdf) of the pending rays of queue b: written by k_lightpdf_list
+                                // (k_extend in the 8-wide build), read by k_shade
+    float *lpdf_out;            // the same for queue b + 1.  k_shade stores the zeros of the rays that miss the light box
+                                // there while other warps still read `lpdf` of queue b: two arrays, like the records
     uint32_t *light_list;       // RT_LIGHT_KERNEL == 2: indices (in the OUT queue) of the pending rays that pass the light box
     uint32_t *light_count;      // [ray_depth + 1] sizes of that list, per queue
 };
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
         }
         dst = __shfl_sync(FULL, dst, 0) + static_cast<uint32_t>(__popc(mask & ((1u << lane) - 1u)));
         lp = __shfl_sync(FULL, lp, 0) + static_cast<uint32_t>(__popc(mp & ((1u << lane) - 1u)));
-        if (pend && !pass) q_store<0>(q.lpdf + dst, 0.0f);
+        if (pend && !pass) q_store<0>(q.lpdf_out + dst, 0.0f);
         if (pass) q.light_list[lp] = dst;
 #else
         if (lane == 0 && mask) dst = atomicAdd(out_counter, static_cast<uint32_t>(__popc(mask)));

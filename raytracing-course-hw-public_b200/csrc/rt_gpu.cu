@@ -108,7 +108,7 @@ template <class T> struct DevBuf {
     }
 };
 
-constexpr size_t kBytesPerPath = 8 * sizeof(float4) + 2 * sizeof(float);  // q_o, q_d, q_thr (x2 parities) + hit + rad + lpdf + light list
+constexpr size_t kBytesPerPath = 8 * sizeof(float4) + 3 * sizeof(float);  // q_o, q_d, q_thr (x2 parities) + hit + rad + lpdf (x2) + light list
 
 enum KernelKind { K_GENERATE = 0, K_EXTEND = 1, K_SHADE = 2, K_ACCUMULATE = 3, K_IDS = 4, K_LIGHTPDF = 5, K_COUNT = 8 };
 
@@ -152,7 +152,7 @@ struct DeviceState {
     DevBuf<uint8_t> arena;
     size_t queue_cap = 0;  // paths the arena holds
     float4 *qo[2] = {nullptr, nullptr}, *qd[2] = {nullptr, nullptr}, *qthr[2] = {nullptr, nullptr}, *hit = nullptr, *rad = nullptr;
-    float *lpdf = nullptr;
+    float *lpdf[2] = {nullptr, nullptr};  // by queue parity, like qo / qd / qthr
     uint32_t *light_list = nullptr;  // RT_LIGHT_KERNEL == 2: queue indices of the pending rays that pass the light box
     DevBuf<float4> accum;
     DevBuf<float> means;   // packed rgb means (rt_gpu_readback)
@@ -169,11 +169,11 @@ struct DeviceState {
         const size_t b16 = up(cap * sizeof(float4)), b4 = up(cap * sizeof(float));
         arena.release();
         queue_cap = 0;
-        if (int rc = arena.alloc(8 * b16 + 2 * b4)) return rc;
+        if (int rc = arena.alloc(8 * b16 + 3 * b4)) return rc;
         uint8_t *p = arena.p;
         if (std::getenv("RT_TIMING"))
             std::fprintf(stderr, "rt_gpu: queue arena %p, %.1f MiB, base mod 512 MiB = %zu MiB\n", static_cast<void *>(p),
-                         (8 * b16 + 2 * b4) / 1048576.0, (reinterpret_cast<size_t>(p) >> 20) & 511);
+                         (8 * b16 + 3 * b4) / 1048576.0, (reinterpret_cast<size_t>(p) >> 20) & 511);
         auto take = [&](size_t b) { uint8_t *r = p; p += b; return r; };
         for (int i = 0; i < 2; ++i) {
             qo[i] = reinterpret_cast<float4 *>(take(b16));
@@ -182,7 +182,8 @@ struct DeviceState {
         }
         hit = reinterpret_cast<float4 *>(take(b16));
         rad = reinterpret_cast<float4 *>(take(b16));
-        lpdf = reinterpret_cast<float *>(take(b4));
+        lpdf[0] = reinterpret_cast<float *>(take(b4));
+        lpdf[1] = reinterpret_cast<float *>(take(b4));
         light_list = reinterpret_cast<uint32_t *>(take(b4));
         queue_cap = cap;
         return RT_OK;
@@ -640,7 +641,8 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
         q.fetch_ext = d.counters.p + (qdepth + 1) * rt::kCounterStride;
         q.fetch_shade = d.counters.p + (2 * qdepth + 1) * rt::kCounterStride;
         q.stats = d.stats.p;
-        q.lpdf = d.lpdf;
+        q.lpdf = d.lpdf[in];
+        q.lpdf_out = d.lpdf[out];
         q.light_list = d.light_list;
         q.light_count = d.counters.p + (3 * qdepth + 1) * rt::kCounterStride;
         return q;

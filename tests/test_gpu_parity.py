@@ -221,6 +221,14 @@ def test_queue_order_and_light_list_do_not_change_the_image(rt, golden_scene):
         del os.environ["RT_NO_TILES"]
     assert np.array_equal(tiled, linear)
     assert st["extension_rays"] == st2["extension_rays"] and st["light_pdf_rays"] == st2["light_pdf_rays"]
+    # k_shade writes the light pdf (0) of the rays it queues while other warps still read the light pdfs of the queue
+    # being shaded: the two live in different arrays (a shared one was a race that moved a few pixels once in a while)
+    rt.render(256, 192, 8, seed=3)
+    first, _ = rt.readback()
+    for _ in range(6):
+        rt.render(256, 192, 8, seed=3)
+        again, _ = rt.readback()
+        assert np.array_equal(first, again)
     if not os.environ.get("RT_GPU_LIB"):  # (an alternative build, e.g. the 8-wide one, keeps the light traversal in k_extend)
         depth = sc.ray_depth
         assert len(sc.light_bvh.objects) > 0
