@@ -276,6 +276,7 @@ int32_t collapse_dp(const DpCollapse &dp, int32_t link, std::vector<WNode> &out)
 
 struct Cnt {
     uint64_t rays = 0, nodes = 0, tris = 0, pops = 0, culled = 0, leaves = 0, pushes = 0;
+    std::vector<uint32_t> per_node;  // optional: visits per wide node
 };
 
 bool tri_hit(const DBvh &bvh, uint32_t k, f3 o, f3 d, float eps, Hit &best) {
@@ -412,6 +413,7 @@ Hit trav_sorted(const std::vector<WNode> &W, int32_t root, int width, const DBvh
     for (;;) {
         if (link >= 0) {
             ++c.nodes;
+            if (!c.per_node.empty()) ++c.per_node[link];
             const WNode &n = W[link];
             float dist[8];
             int32_t ls[8];
@@ -471,6 +473,67 @@ void report(const char *name, const Cnt &c) {
 }
 }  // namespace
 
+// Child boxes of a wide-node array replaced by what an 8-bit-per-plane encoding would decode to (conservative:
+// every decoded box contains the exact one).  mode 0: the library's grid (power-of-two cell, 1/64-cell margin, origin
+// with 14 mantissa bits); mode 1: cell = extent / 255 exactly (a float scale per axis), origin = the node's minimum;
+// mode 2: like 0 without the margin; mode 3: 16 bits per plane on the power-of-two grid.
+std::vector<WNode> requant(const std::vector<WNode> &W, int mode) {
+    std::vector<WNode> out = W;
+    for (WNode &n : out) {
+        if (mode >= 4) {  // 4: exact boxes moved outward by one ulp; 5: by 1e-5 of the node's extent
+            for (int k = 0; k < 3; ++k) {
+                float mn = 1e30f, mx = -1e30f;
+                for (int s = 0; s < 8; ++s)
+                    if (n.ch[s].link != RT_LINK_NONE) mn = std::min(mn, n.ch[s].lo[k]), mx = std::max(mx, n.ch[s].hi[k]);
+                for (int s = 0; s < 8; ++s) {
+                    WChild &c = n.ch[s];
+                    if (c.link == RT_LINK_NONE) continue;
+                    if (mode == 4) c.lo[k] = std::nextafterf(c.lo[k], -INFINITY), c.hi[k] = std::nextafterf(c.hi[k], INFINITY);
+                    else c.lo[k] -= 1e-5f * (mx - mn), c.hi[k] += 1e-5f * (mx - mn);
+                }
+            }
+            continue;
+        }
+        for (int k = 0; k < 3; ++k) {
+            double mn = 1e300, mx = -1e300;
+            for (int s = 0; s < 8; ++s)
+                if (n.ch[s].link != RT_LINK_NONE) mn = std::min<double>(mn, n.ch[s].lo[k]), mx = std::max<double>(mx, n.ch[s].hi[k]);
+            if (mn > mx) continue;
+            const double ext = mx - mn;
+            const double steps = mode == 3 ? 65535.0 : 255.0;
+            double cell, org, margin = (mode == 0) ? 1.0 / 64.0 : 0.0;
+            if (mode == 1) {
+                cell = ext > 0 ? ext / steps * (1.0 + 1e-6) : 1e-30;
+                org = mn;
+            } else {
+                int e = ext > 0 ? (int)std::ceil(std::log2(ext / steps * (1.0 + 2.0 * margin / steps + 1e-9))) : -100;
+                cell = std::ldexp(1.0, e);
+                org = mn - margin * cell;
+                if (mode == 0) {  // origin rounded down to 14 mantissa bits (the low 9 bits of the word hold the exponent)
+                    float of = (float)org;
+                    if ((double)of > org) of = std::nextafterf(of, -INFINITY);
+                    uint32_t b;
+                    std::memcpy(&b, &of, 4);
+                    if (of >= 0) b &= ~0x1FFu; else b = (b | 0x1FFu);
+                    std::memcpy(&of, &b, 4);
+                    org = of;
+                    while ((mx - org) / cell + margin > steps) cell *= 2.0;
+                }
+            }
+            for (int s = 0; s < 8; ++s) {
+                WChild &c = n.ch[s];
+                if (c.link == RT_LINK_NONE) continue;
+                const double a = std::floor((c.lo[k] - org) / cell - margin), z = std::ceil((c.hi[k] - org) / cell + margin);
+                c.lo[k] = (float)(org + a * cell);
+                if ((double)c.lo[k] > org + a * cell) c.lo[k] = std::nextafterf(c.lo[k], -INFINITY);
+                c.hi[k] = (float)(org + z * cell);
+                if ((double)c.hi[k] < org + z * cell) c.hi[k] = std::nextafterf(c.hi[k], INFINITY);
+            }
+        }
+    }
+    return out;
+}
+
 extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint32_t spp) {
     PackedScene p;
     if (int rc = pack_scene(*sc, p, true)) return rc;
@@ -512,7 +575,11 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     c.tan_half_y = tanf(atanf(tanf(d.fov_x / 2) * (float)h / (float)w));
     c.inv_w2 = 2.0f / (float)w;
     c.inv_h2 = 2.0f / (float)h;
+    const std::vector<WNode> W4q0 = requant(W4, 0), W4q1 = requant(W4, 1), W4q2 = requant(W4, 2), W4q3 = requant(W4, 3), W4q4 = requant(W4, 4), W4q5 = requant(W4, 5);
+    Cnt aq0, aq1, aq2, aq3, aq4, aq5;
     Cnt a4, b4, b4d, a8, b8, b8d, q4, b8o, a4o, a4m, a4m2;
+    a4.per_node.assign(W4.size(), 0);
+    aq5.per_node.assign(W4.size(), 0);
     uint64_t mism = 0;
     for (uint32_t pix = 0; pix < w * h; ++pix)
         for (uint32_t s = 0; s < spp; ++s) {
@@ -536,6 +603,12 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
                 trav_sorted(W4d, r4d, 4, d.scene, o, dir, d.eps, a4o);
                 trav_sorted(W4, r4, 4, d.scene, o, dir, d.eps, a4m, 1);
                 trav_sorted(W4, r4, 4, d.scene, o, dir, d.eps, a4m2, 2);
+                trav_sorted(W4q0, r4, 4, d.scene, o, dir, d.eps, aq0);
+                trav_sorted(W4q1, r4, 4, d.scene, o, dir, d.eps, aq1);
+                trav_sorted(W4q2, r4, 4, d.scene, o, dir, d.eps, aq2);
+                trav_sorted(W4q3, r4, 4, d.scene, o, dir, d.eps, aq3);
+                trav_sorted(W4q4, r4, 4, d.scene, o, dir, d.eps, aq4);
+                trav_sorted(W4q5, r4, 4, d.scene, o, dir, d.eps, aq5);
                 mism += (h1.tri != hit.tri) + (h2.tri != hit.tri) + (h3.tri != hit.tri);
                 uint32_t lr = 0;
                 if (!shade_bounce(d, p.gamma_lut, key, b, b + 1 == d.ray_depth, hit, o, dir, thr, rad, lr)) break;
@@ -553,5 +626,32 @@ extern "C" int wide_study(const rt_scene_desc *sc, uint32_t w, uint32_t h, uint3
     report("A4 cost-optimal collapse, sorted", a4o);
     report("A4 nearest first, rest unsorted", a4m);
     report("A4 nearest first, farthest last", a4m2);
+    report("A4 boxes as the library quantises", aq0);
+    report("A4 8 bit, exact cell = extent/255", aq1);
+    report("A4 8 bit, power-of-two, no margin", aq2);
+    report("A4 16 bit planes, power-of-two", aq3);
+    report("A4 exact boxes + 1 ulp outward", aq4);
+    report("A4 exact boxes + 1e-5 extent", aq5);
+    {   // where do the extra visits of the slightly widened boxes happen?
+        std::vector<int> depth(W4.size(), 0), order;
+        std::vector<int32_t> st{r4};
+        while (!st.empty()) {
+            const int32_t n = st.back();
+            st.pop_back();
+            for (int s = 0; s < 4; ++s)
+                if (W4[n].ch[s].link != RT_LINK_NONE && W4[n].ch[s].link >= 0) depth[W4[n].ch[s].link] = depth[n] + 1, st.push_back(W4[n].ch[s].link);
+        }
+        uint64_t by_depth_a[32] = {0}, by_depth_b[32] = {0};
+        for (size_t i = 0; i < W4.size(); ++i) by_depth_a[std::min(depth[i], 31)] += a4.per_node[i], by_depth_b[std::min(depth[i], 31)] += aq5.per_node[i];
+        for (int dd = 0; dd < 14; ++dd) std::printf("depth %2d: exact %8llu  widened %8llu\n", dd, (unsigned long long)by_depth_a[dd], (unsigned long long)by_depth_b[dd]);
+        size_t worst = 0;
+        for (size_t i = 0; i < W4.size(); ++i)
+            if ((int64_t)aq5.per_node[i] - a4.per_node[i] > (int64_t)aq5.per_node[worst] - a4.per_node[worst]) worst = i;
+        std::printf("node %zu depth %d: %u -> %u visits\n", worst, depth[worst], a4.per_node[worst], aq5.per_node[worst]);
+        for (int s = 0; s < 4; ++s) {
+            const WChild &c = W4[worst].ch[s];
+            if (c.link != RT_LINK_NONE) std::printf("  child %d link %d lo %.6f %.6f %.6f hi %.6f %.6f %.6f\n", s, c.link, c.lo[0], c.lo[1], c.lo[2], c.hi[0], c.hi[1], c.hi[2]);
+        }
+    }
     return 0;
 }
