@@ -157,7 +157,7 @@ typedef struct rt_render_params {
     uint32_t sample_end;     /* 0 => samples */
     uint32_t mode;           /* rt_render_mode */
     uint64_t seed;           /* Philox key */
-    uint32_t max_paths_in_flight; /* 0 => default: 512 Mi paths (132 B of queue state each = 71 GB), at most half of the
+    uint32_t max_paths_in_flight; /* 0 => default: 512 Mi paths (140 B of queue state each = 75 GB), at most half of the
                                      free device memory; callers that share the device (torch, NCCL) pass a bound */
     uint32_t flags;          /* RT_FLAG_* */
     uint32_t pixel_begin;    /* this call renders the row-major pixels [pixel_begin, pixel_end) only (the other */

@@ -602,7 +602,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
     // Paths in flight per batch.  Every kernel of a batch ends with a tail in which the last warps finish
     // their rays while the other SMs idle, so throughput grows with the batch: 8 Mi / 16 / 32 / 64 / 128 /
     // 256 Mi paths -> 771 / 819 / 845 / 881 / 896 / 910 Msamples/s on config 4 (B200, measured; a later build: 128 / 256 /
-    // 512 / 640 Mi -> 1149 / 1163 / 1169 / 1169).  The default is 512 Mi paths (132 B of queue state each = 71 GB of the
+    // 512 / 640 Mi -> 1149 / 1163 / 1169 / 1169).  The default is 512 Mi paths (140 B of queue state each = 75 GB of the
     // 180 GB), capped at half of the free memory.
     const size_t px_begin = ids_mode ? 0 : rp.pixel_begin, px_end = ids_mode || rp.pixel_end == 0 ? n_pix : rp.pixel_end;
     const size_t n_render = px_end - px_begin;  // image-tile split: only this pixel range is rendered
