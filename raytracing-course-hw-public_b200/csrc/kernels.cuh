@@ -65,6 +65,20 @@ struct Queues {
     uint32_t *light_count;      // [ray_depth + 1] sizes of that list, per queue
 };
 
+// A launch of k_extend / k_shade handles the whole queue or one half of it: the host runs the two halves on two streams
+// so that one half's kernels fill the SMs the other half's draining kernel leaves idle (rt_gpu.cu); each half has its
+// own work-fetch cursors (fetch_ext / fetch_shade point at them).  The part travels in the high bits of the kernels'
+// `bounce` argument (kPartFirst / kPartSecond): growing the Queues parameter by two words cost k_shade eight registers.
+constexpr uint32_t kPartShift = 16, kPartFirst = 1u << kPartShift, kPartSecond = 2u << kPartShift;
+// [part_begin, part_end) of the queue entries a launch handles; the halves meet at a multiple of 128 (k_extend's ray
+// block).  The begin is a function of the end, so that the kernels need not keep it in a register.
+__device__ __forceinline__ uint32_t part_end(uint32_t part, uint32_t count) {
+    return part == kPartFirst ? (count >> 1) & ~127u : count;
+}
+__device__ __forceinline__ uint32_t part_begin(uint32_t part, uint32_t end) {  // end = part_end(part, count)
+    return part == kPartSecond ? (end >> 1) & ~127u : 0u;
+}
+
 // Queue records are read once and written once per bounce (streaming), the scene is re-read by every ray: with
 // RT_QUEUE_STREAMING the queue accesses carry the evict-first hint (ld/st.global.cs) so that they do not push nodes,
 // triangles and attributes out of the L2.  Measured on the B200 (k_extend / k_shade ms per 128 spp): off 84.9 / 25.7,
@@ -253,11 +267,12 @@ template <int H> __device__ __forceinline__ f4 ld4h(const void *p) {
 __device__ __forceinline__ bool link_is_leaf(int32_t link) { return link < 0 && link != kLinkDone && link != kLinkPop; }
 
 __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
-    k_extend(DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce,
+    k_extend(DBvh bvh, DBvh lbvh, const DLight *__restrict__ light_extra, float inv_n_lights, float eps, Queues q, uint32_t bounce_part,
              uint32_t one) {
     // `one` = 0x3F800000, passed as an argument so that it is not an immediate (see qplane() in pt_core.cuh)
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t count = q.count[bounce * kCounterStride];
+    const uint32_t part = bounce_part & ~(kPartFirst - 1u), bounce = bounce_part & (kPartFirst - 1u);
+    const uint32_t count = part_end(part, q.count[bounce * kCounterStride]);  // this launch's part of the queue: [part_begin, count)
     const float4 *__restrict__ qo = q.o_in;
     const float4 *__restrict__ qd = q.d_in;
     uint32_t *cursor = q.fetch_ext + bounce * kCounterStride;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(kExtendThreads, RT_EXT_MINB)
             if (pool_next == pool_end && !exhausted) {  // one atomicAdd per kRayBlock rays
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(cursor, kRayBlock);
-                base = __shfl_sync(FULL, base, 0);
+                base = __shfl_sync(FULL, base, 0) + part_begin(part, count);
                 if (base >= count) {
                     exhausted = true;
                 } else {
@@ -645,12 +660,13 @@ __global__ void __launch_bounds__(kShadeThreads, RT_SHADE_MINB) k_shade(
 #else
 __global__ void __launch_bounds__(kShadeThreads) k_shade(
 #endif
-    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q, uint32_t bounce, LightBox light_box) {
+    DScene s, const float *__restrict__ lut_g, BatchParams bp, Queues q, uint32_t bounce_part, LightBox light_box) {
     __shared__ float lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = lut_g[i];
     __syncthreads();
     const uint32_t FULL = 0xFFFFFFFFu;
-    const uint32_t count = q.count[bounce * kCounterStride];
+    const uint32_t part = bounce_part & ~(kPartFirst - 1u), bounce = bounce_part & (kPartFirst - 1u);
+    const uint32_t count = part_end(part, q.count[bounce * kCounterStride]);  // this launch's part of the queue: [part_begin, count)
     uint32_t *const fetch_cursor = q.fetch_shade + bounce * kCounterStride;
     uint32_t *const out_counter = q.count + (bounce + 1) * kCounterStride;
     const bool last = bounce + 1 == s.ray_depth;
@@ -663,7 +679,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
     // DTri / DAttr lines are prefetched at the end of the iteration).
     uint32_t base_w = 0, ahead = 0;
     if (lane == 0) base_w = atomicAdd(fetch_cursor, 32u);
-    base_w = __shfl_sync(FULL, base_w, 0);
+    base_w = __shfl_sync(FULL, base_w, 0) + part_begin(part, count);
     if (lane == 0) ahead = atomicAdd(fetch_cursor, 32u);
 #endif
     for (;;) {
@@ -672,7 +688,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
 #else
         uint32_t base = 0;  // the warp pulls the next 32 queue entries
         if (lane == 0) base = atomicAdd(fetch_cursor, 32u);
-        base = __shfl_sync(FULL, base, 0);
+        base = __shfl_sync(FULL, base, 0) + part_begin(part, count);
 #endif
         if (base >= count) break;
         const uint32_t i = base + lane;
@@ -732,7 +748,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade(
         }
 #if RT_SHADE_PREFETCH
         // the next iteration's records -> L1; request the cursor value of the iteration after it
-        base_w = __shfl_sync(FULL, ahead, 0);
+        base_w = __shfl_sync(FULL, ahead, 0) + part_begin(part, count);
         if (lane == 0) ahead = atomicAdd(fetch_cursor, 32u);
         const uint32_t i_next = base_w + lane;
 #if RT_SHADE_PREFETCH >= 2

@@ -117,6 +117,9 @@ struct DeviceState {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the triangle attributes while the BVH build runs on `stream`
+    cudaStream_t stream2 = nullptr;      // second half of every queue (enqueue_render): its kernels fill the SMs that the
+                                         // first half's draining persistent kernel leaves idle, and vice versa
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_light = nullptr;  // cross-stream ordering of the two halves
     cudaEvent_t ev_copied = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_red0 = nullptr, ev_red1 = nullptr;
     // scene
@@ -622,7 +625,7 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
     const size_t cap = std::min(max_paths, want_total);
     if (int rc = d.alloc_queues(cap)) return rc;
     const uint32_t qdepth = std::max(depth, 1u);
-    const size_t n_counters = (4 * static_cast<size_t>(qdepth) + 2) * rt::kCounterStride;  // one 256-byte line each
+    const size_t n_counters = (6 * static_cast<size_t>(qdepth) + 2) * rt::kCounterStride;  // one 256-byte line each
     if (int rc = d.counters.alloc(n_counters)) return rc;
 
     // Queues of bounce b: in = parity b & 1, out = the other one (k_generate fills queue 0 through `out` of b = -1)
@@ -648,6 +651,8 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
         return q;
     };
     const rt::Queues q_gen = queues_of(-1);
+    // per-kernel profiling needs the kernels one after the other on one stream
+    const bool split_allowed = !ids_mode && !ctx->profiling && !std::getenv("RT_NO_SPLIT");
 
     const float inv_n_lights = d.scene.n_lights ? 1.0f / static_cast<float>(d.scene.n_lights) : 0.0f;
     rt::BatchParams bp;
@@ -680,6 +685,47 @@ int enqueue_render(rt_gpu_ctx *ctx, DeviceState &d, int dev_index, const rt_rend
                 launches += 3;
                 continue;
             }
+#if !RT_EXT_WIDE8
+            // Batches below 256 Mi paths: two halves of every queue on two streams.  A persistent kernel ends with a drain
+            // (once its queue is empty every warp runs on with fewer and fewer live lanes and the SMs empty out), a fixed
+            // cost per launch.  With the halves in flight together the other half's next kernel moves into the freed
+            // slots: E(b, 0) | E(b, 1) over E(b, 0)'s drain | S(b, 0) over E(b, 1)'s drain | S(b, 1) over S(b, 0)'s; only
+            // the last shade of a bounce drains in the open (both halves of queue b + 1 need both shades of queue b).
+            // Measured on config 4: 92.05 -> 91.07 ms at 125 spp (the 8-GPU share of the image), 709.7 -> 711.6 ms at
+            // 1000 spp in 512 Mi-path batches, hence the bound.
+            const bool split = split_allowed && n < (256u << 20);
+            if (split) {
+                cudaStream_t sa = d.stream, sb = d.stream2;
+                CU_CHECK(cudaEventRecord(d.ev_a, sa));  // k_generate (and the counters' memset) done
+                CU_CHECK(cudaStreamWaitEvent(sb, d.ev_a, 0));
+                for (uint32_t b = 0; b < depth; ++b) {
+                    rt::Queues q0 = queues_of(static_cast<int>(b)), q1 = q0;
+                    q1.fetch_ext = d.counters.p + (4 * qdepth + 2) * rt::kCounterStride;
+                    q1.fetch_shade = d.counters.p + (5 * qdepth + 2) * rt::kCounterStride;
+                    if (b > 0) {  // queue b is complete when both shades of queue b - 1 are
+                        CU_CHECK(cudaStreamWaitEvent(sa, d.ev_b, 0));
+                        CU_CHECK(cudaStreamWaitEvent(sb, d.ev_a, 0));
+                    }
+                    const bool light = RT_LIGHT_KERNEL && b > 0 && d.scene.n_lights > 0;
+                    if (light) {
+                        rt::k_lightpdf_list<<<d.light_blocks, rt::kLightThreads, 0, sa>>>(d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q0, b, 0x3F800000u);
+                        CU_CHECK(cudaEventRecord(d.ev_light, sa));
+                        ++launches;
+                    }
+                    rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, sa>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q0, b | rt::kPartFirst, 0x3F800000u);
+                    rt::k_extend<<<d.extend_blocks, rt::kExtendThreads, 0, sb>>>(d.scene.scene, d.scene.light, d.scene.light_extra, inv_n_lights, d.scene.eps, q1, b | rt::kPartSecond, 0x3F800000u);
+                    rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, sa>>>(d.scene, d.lut.p, bp, q0, b | rt::kPartFirst, d.light_box);
+                    if (light) CU_CHECK(cudaStreamWaitEvent(sb, d.ev_light, 0));  // the light pdfs of queue b
+                    rt::k_shade<<<d.shade_blocks, rt::kShadeThreads, 0, sb>>>(d.scene, d.lut.p, bp, q1, b | rt::kPartSecond, d.light_box);
+                    CU_CHECK(cudaEventRecord(d.ev_a, sa));
+                    CU_CHECK(cudaEventRecord(d.ev_b, sb));
+                }
+                CU_CHECK(cudaStreamWaitEvent(sa, d.ev_b, 0));
+                rt::k_accumulate<<<(bp.npix + 255) / 256, 256, 0, sa>>>(bp, d.rad, d.accum.p);
+                launches += 2 + 4 * static_cast<uint64_t>(depth);
+                continue;
+            }
+#endif
             for (uint32_t b = 0; b < depth; ++b) {
                 const rt::Queues q = queues_of(static_cast<int>(b));
 #if RT_LIGHT_KERNEL
@@ -735,6 +781,10 @@ int create_devices(rt_gpu_ctx *ctx, int n_gpus, int first_device) {
         d->sm_count = prop.multiProcessorCount;
         CU_CHECK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
         CU_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+        CU_CHECK(cudaEventCreateWithFlags(&d->ev_a, cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&d->ev_b, cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&d->ev_light, cudaEventDisableTiming));
         CU_CHECK(cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming));
         CU_CHECK(cudaEventCreate(&d->ev_begin));
         CU_CHECK(cudaEventCreate(&d->ev_end));
@@ -799,6 +849,7 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         if (!dp || !dp->stream) continue;
         cudaSetDevice(dp->device);
         cudaStreamSynchronize(dp->stream);
+        if (dp->stream2) cudaStreamSynchronize(dp->stream2);
     }
     for (ncclComm_t c : ctx->comms)
         if (c) g_nccl.CommDestroy(c);
@@ -818,8 +869,9 @@ void rt_gpu_destroy(rt_gpu_ctx *ctx) {
         d.counters.release(); d.stats.release();
         d.prim_ids.release(); d.rgb8.release();
         for (cudaEvent_t e : d.event_pool) cudaEventDestroy(e);
-        for (cudaEvent_t e : {d.ev_begin, d.ev_end, d.ev_red0, d.ev_red1})
+        for (cudaEvent_t e : {d.ev_begin, d.ev_end, d.ev_red0, d.ev_red1, d.ev_a, d.ev_b, d.ev_light})
             if (e) cudaEventDestroy(e);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.ev_copied) cudaEventDestroy(d.ev_copied);
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.stream) cudaStreamDestroy(d.stream);

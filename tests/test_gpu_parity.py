@@ -232,14 +232,23 @@ def test_queue_order_and_light_list_do_not_change_the_image(rt, golden_scene):
     if not os.environ.get("RT_GPU_LIB"):  # (an alternative build, e.g. the 8-wide one, keeps the light traversal in k_extend)
         depth = sc.ray_depth
         assert len(sc.light_bvh.objects) > 0
-        # one batch: k_generate, depth x (k_extend + k_shade), k_accumulate, k_lightpdf_list for queues 1 .. depth - 1
-        assert st["kernel_launches"] == 2 + 2 * depth + (depth - 1)
+        # one small batch: k_generate, k_accumulate, k_lightpdf_list for queues 1 .. depth - 1, and k_extend + k_shade
+        # once per HALF of every queue (two streams) — or once per queue with RT_NO_SPLIT=1; same image bit for bit
+        assert st["kernel_launches"] == 2 + 4 * depth + (depth - 1)
+        os.environ["RT_NO_SPLIT"] = "1"
+        try:
+            rt.render(w, h, s, seed=11)
+            whole, st4 = rt.readback()
+        finally:
+            del os.environ["RT_NO_SPLIT"]
+        assert st4["kernel_launches"] == 2 + 2 * depth + (depth - 1)
+        assert np.array_equal(whole, tiled) and st4["extension_rays"] == st["extension_rays"]
         sc2 = golden_scene("tiny")
         rt.upload_scene(sc2)
         rt.render(40, 32, 2, seed=1)
         _, st3 = rt.readback()
         lights = len(sc2.light_bvh.objects) > 0
-        assert st3["kernel_launches"] == 2 + 2 * sc2.ray_depth + ((sc2.ray_depth - 1) if lights else 0)
+        assert st3["kernel_launches"] == 2 + 4 * sc2.ray_depth + ((sc2.ray_depth - 1) if lights else 0)
 
 
 def test_pixel_range_renders_add_up(rt, golden_scene):
