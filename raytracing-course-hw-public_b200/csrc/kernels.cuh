@@ -1,13 +1,15 @@
 // kernels.cuh — the wavefront kernels (sm_100a).  One "batch" = npix pixels x k samples = N paths:
 //
-//   k_generate   N paths: Philox pixel jitter -> camera ray (gen_ray, raytracer.h:527-538)
+//   k_generate   N paths: Philox pixel jitter -> camera ray (gen_ray, raytracer.h:527-538), 8 x 4 pixel tiles per warp
 //   for bounce b in [0, ray_depth):
-//     k_extend   closest-hit BVH traversal of queue b (cast_ray -> BVH::intersect_ray, bvh.h:170-235); for a
-//                "pending" ray first the all-hit traversal of the light BVH (bvh_mix_dist::pdf, raytracer.h:363)
+//     k_lightpdf_list  (b > 0, scenes with lights) all-hit traversal of the light BVH (bvh_mix_dist::pdf,
+//                raytracer.h:363) for the pending rays of queue b that k_shade(b - 1) found inside the box of all lights
+//     k_extend   closest-hit BVH traversal of queue b (cast_ray -> BVH::intersect_ray, bvh.h:170-235)
 //     k_shade    resolve the previous bounce with that light pdf, hit data + shade() state transition
 //                (raytracer.h:555-591), survivors compacted into queue b+1 with warp-aggregated
-//                (__ballot/__popc) appends
+//                (__ballot/__popc) appends; light-box test of the rays it queues
 //   k_accumulate per-sample NaN scrub + per-pixel float sums (render_pixel, raytracer.h:607-627)
+// Small batches run k_extend / k_shade once per HALF of a queue, the halves on two streams (rt_gpu.cu, enqueue_render).
 //
 // Path state is SoA of float4 (128-bit coalesced loads/stores), ping-ponged between queue b and b+1:
 //   q_o   = (origin.xyz,     pixel index bits)
@@ -15,10 +17,12 @@
 //   q_thr = (throughput.rgb [x f_cos when pending], p_partial >= 0 when the path's pdf still needs the light
 //            pdf of this ray ("pending", also bit 31 of the sample index), else -1)
 //   hit   = (t, beta, gamma, BVH-order triangle index bits or -1)      written by extend, read by shade
-//   lpdf  = light pdf of the queued ray                                 written by extend for pending rays
+//   lpdf  = light pdf of the queued ray, one array per queue parity     written by shade (0: outside the light box) and
+//           k_lightpdf_list for the pending rays of the queue, read by the next shade
+//   llist = queue indices of the pending rays inside the light box      written by shade, read by k_lightpdf_list
 //   rad   = per-path radiance accumulator, indexed by the path's fixed slot (no atomics: one owner)
-// extend and shade are persistent: grid = SMs x resident CTAs, each warp pulls 32 queue entries at a
-// time from a device counter, so no host round trip is needed to size a launch.
+// extend and shade are persistent: grid = SMs x resident CTAs, each warp pulls queue entries (128 / 32 at a time) from
+// a device counter, so no host round trip is needed to size a launch.
 #ifndef RT_KERNELS_CUH
 #define RT_KERNELS_CUH
 
@@ -175,10 +179,10 @@ __device__ __forceinline__ float light_pdf_term(f3 d, float t, f4 le) {
 // Visiting order (near child first, ties left first, bvh.h:216) and strictly-closer-wins (bvh.h:132)
 // are those of closest_hit_q4() in pt_core.cuh, so both give the same hit.
 //
-// A pending ray (bit 31 of its sample index) is traversed twice: first through the light BVH, all hits, summing
-// bvh_mix_dist::pdf (raytracer.h:363-375; best_t stays +inf, so nothing is culled), then through the scene BVH for
-// the closest hit.  Both run in the same warp-synchronous loops; the lane goes from the one into the other inside
-// the pop step, without waiting for a refill section.
+// With RT_LIGHT_KERNEL == 0 (the 8-wide build's setting; the default until r2_v4) a pending ray (bit 31 of its sample
+// index) is traversed twice: first through the light BVH, all hits, summing bvh_mix_dist::pdf (raytracer.h:363-375;
+// best_t stays +inf, so nothing is culled), then through the scene BVH for the closest hit, both in the same
+// warp-synchronous loops.  By default the light query runs in k_lightpdf_list and this kernel sees scene rays only.
 //
 // Compile-time knobs (A/B-tested on the B200, DESIGN.md "k_extend"; defaults = the fastest measured).  Alternatives
 // that were measured and removed from the source: 2-wide 32-byte nodes, 64-byte full-precision nodes, node step before
