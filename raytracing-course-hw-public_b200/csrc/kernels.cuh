@@ -104,7 +104,10 @@ template <int BIT> __device__ __forceinline__ void q_store(float *p, float v) {
     else *p = v;
 }
 
-constexpr int kExtendThreads = 128;
+#ifndef RT_EXT_THREADS
+#define RT_EXT_THREADS 128  // threads per CTA of k_extend (and k_extend8)
+#endif
+constexpr int kExtendThreads = RT_EXT_THREADS;
 constexpr int kShadeThreads = 128;
 #ifndef RT_COUNTER_STRIDE
 #define RT_COUNTER_STRIDE 64  // uint32 per counter slot (256 B); 1 = packed (round 1)
