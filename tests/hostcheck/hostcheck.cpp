@@ -400,6 +400,23 @@ int hc_primary_ids_q4(const rt_scene_desc *sc, uint32_t w, uint32_t h, int32_t *
     return 0;
 }
 
+// Arbitrary rays (n x 6 floats: origin, direction) through the exact binary tree and through the quantised 4-wide nodes
+// in the kernel's arithmetic: tri_exact / tri_q4 = BVH-order triangle or -1, t_exact / t_q4 = hit distance (inf: miss).
+int hc_trace_rays(const rt_scene_desc *sc, uint64_t n, const float *rays, int32_t *tri_exact, float *t_exact, int32_t *tri_q4, float *t_q4) {
+    HostScene hs;
+    if (int rc = build(sc, hs)) return rc;
+    for (uint64_t i = 0; i < n; ++i) {
+        const f3 o = mk3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), d = mk3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]);
+        const Hit a = closest_hit(hs.d.scene, o, d, hs.d.eps);
+        const Hit b = closest_hit_q4(hs.d.scene, o, d, hs.d.eps, nullptr);
+        tri_exact[i] = a.tri;
+        t_exact[i] = a.t;
+        tri_q4[i] = b.tri;
+        t_q4[i] = b.t;
+    }
+    return 0;
+}
+
 // Wall time of the re-pack phases (ms): out[0] SAH build, out[1] pack_bvh of the scene tree (triangles, nodes, both
 // quantisations, collapse), out[2] whole pack_scene with rebuild, out[3] the upload path's pack_scene (4-wide only),
 // out[4..7] its phases.

@@ -284,6 +284,51 @@ def test_four_wide_collapse_gives_reference_ids(name, rebuild, hc, manifest, gol
     assert steps[0] <= steps[1]  # never more node steps than the binary traversal
 
 
+def test_rays_inside_the_plane_of_a_flat_node_keep_their_hits(hc, big_scene):
+    """Light-sampled directions from one emissive panel to the next run INSIDE the panels' common plane (|d.y| ~ 1e-7,
+    origin one ulp above it): the ray-space offset fma(org, 1/d, -o/d) of the quantised slab test then carries an
+    error of several units of t, and a flat node's box has to absorb it.  The power-of-two grid does (its origin is
+    rounded down to 14 mantissa bits, which leaves every flat box ~2e-6 of slack); an exact-cell variant tried in round 2
+    lost 33 of 15 176 path-traced rays exactly here (k_extend).  Every hit the exact boxes find must be
+    found through the quantised 4-wide nodes as well."""
+    sc = big_scene
+    lights = np.asarray(sc.light_bvh.objects, np.int64)
+    assert len(lights) >= 8
+    rng = np.random.default_rng(5)
+    tri = sc.tri_pos[lights].astype(np.float64)  # (n, 3, 3)
+
+    def points(idx):
+        u, v = rng.random(len(idx)), rng.random(len(idx))
+        flip = u + v > 1
+        u[flip], v[flip] = 1 - u[flip], 1 - v[flip]
+        t = tri[idx]
+        return t[:, 0] + (t[:, 1] - t[:, 0]) * u[:, None] + (t[:, 2] - t[:, 0]) * v[:, None]
+
+    n = 4000
+    a, b = rng.integers(0, len(lights), n), rng.integers(0, len(lights), n)
+    o, q = points(a), points(b)
+    keep = np.linalg.norm(q - o, axis=1) > 0.5
+    o, q = o[keep], q[keep]
+    o32 = o.astype(np.float32)
+    o32[:, 1] = np.nextafter(o32[:, 1], np.float32(np.inf))  # one ulp above the panels' plane, like a hit point
+    d = q - o32.astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.ascontiguousarray(np.concatenate([o32, d.astype(np.float32)], axis=1), np.float32)
+    m = len(rays)
+    te, tq = np.zeros(m, np.float32), np.zeros(m, np.float32)
+    ie, iq = np.zeros(m, np.int32), np.zeros(m, np.int32)
+    desc = sc.desc()
+    hc.hc_set_rebuild(1)
+    try:
+        assert hc.hc_trace_rays(C.byref(desc), C.c_uint64(m), rays.ctypes.data_as(C.c_void_p), ie.ctypes.data_as(C.c_void_p),
+                                te.ctypes.data_as(C.c_void_p), iq.ctypes.data_as(C.c_void_p), tq.ctypes.data_as(C.c_void_p)) == 0
+    finally:
+        hc.hc_set_rebuild(0)
+    assert (ie >= 0).mean() > 0.5  # these rays do hit something (walls, columns, other panels)
+    lost = (ie >= 0) & ((iq < 0) | (tq > te * (1 + 1e-4)))
+    assert lost.sum() == 0, f"{int(lost.sum())} of {m} in-plane rays lose their hit through the quantised nodes"
+
+
 def test_four_wide_collapse_on_the_260k_scene(hc, big_scene):
     d = big_scene.desc()
     ids4 = np.zeros((96, 96), np.int32)
