@@ -11,6 +11,7 @@ Scenes
   tiny         7 triangles, Cornell-like: floor, back wall, emissive triangle, metallic quad
   small        scaled-down corridor (~2.7k triangles), env lit
   small_lights same + 32 emissive triangles
+  small_manylights  same with the four panels cut into 12 x 12 quads: 1152 emissive triangles (a light BVH several levels deep)
   big          "Sponza-scale" corridor, 260 160 triangles, env lit
   big_lights   same + 32 emissive triangles = 260 192
   texmaps      texall with every roughness >= 0.35 (well-conditioned: held to the tight path-by-path bound)
@@ -189,8 +190,9 @@ def grid(nu, nv, fn):
     return P.reshape(-1, 3), N.reshape(-1, 3), uv.reshape(-1, 2), tris
 
 
-def corridor(name, scale, lights):
-    """Corridor 16 x 60 x 12 m open to the sky. scale=1 -> 260 160 triangles."""
+def corridor(name, scale, lights, light_res=2):
+    """Corridor 16 x 60 x 12 m open to the sky. scale=1 -> 260 160 triangles.  light_res: quads per side of each of the
+    four emissive panels (2 -> 8 triangles per panel)."""
     rng = np.random.default_rng(260000)
     g = GltfBuilder(name)
     W, L, H = 16.0, 60.0, 12.0
@@ -278,7 +280,7 @@ def corridor(name, scale, lights):
             def panel(u, v, cz=cz):
                 return np.stack([(u - 0.5) * 2.0, np.full_like(u, 8.0), cz + (v - 0.5) * 2.0], -1)
 
-            P, N, UV, T = grid(2, 2, panel)
+            P, N, UV, T = grid(light_res, light_res, panel)
             add(P, N, UV, T, m_light)
 
     g.node(mesh=g.mesh(prims))
@@ -396,6 +398,7 @@ SCENES = {
     "texmaps": lambda: texall("texmaps", 0.35),
     "small": lambda: corridor("small", 0.1, False),
     "small_lights": lambda: corridor("small_lights", 0.1, True),
+    "small_manylights": lambda: corridor("small_manylights", 0.1, True, light_res=12),  # 4 x 288 emissive triangles: a deep light BVH
     "medium_lights": lambda: corridor("medium_lights", 0.3, True),
     "big": lambda: corridor("big", 1.0, False),
     "big_lights": lambda: corridor("big_lights", 1.0, True),

@@ -581,6 +581,25 @@ def _follow_oracle_paths(name, tol_frac, hc, manifest, golden_scene):
     assert abs(cnt[0] - st["extension_rays"]) <= 0.02 * st["extension_rays"]
 
 
+def test_many_lights_scene_follows_oracle_paths(hc, scene_dir):
+    """1152 emissive triangles (a light BVH five wide levels deep, every bounce samples and queries it): the host
+    compilation of the device math follows the pinned oracle path by path, like the GPU test of the same scene."""
+    from rt_b200 import gltf
+
+    sc = gltf.load_gltf(scene_dir("small_manylights"), 1.0)
+    assert len(sc.light_bvh.objects) == 1152
+    d = sc.desc()
+    w, h, spp, seed = 48, 36, 8, 5
+    out = np.zeros((h, w, 3), np.float32)
+    cnt = (C.c_uint64 * 2)()
+    assert hc.hc_render(C.byref(d), w, h, spp, 0, spp, C.c_uint64(seed), out.ctypes.data_as(C.c_void_p), cnt) == 0
+    ref, st = O.render(sc, w, h, spp, rng_mode=O.RNG_PHILOX, seed=seed)
+    rel = (np.abs(out - ref) / (np.abs(ref) + 1e-3)).max(axis=2)
+    assert (rel > 1e-3).mean() <= 0.08
+    assert abs(np.mean(out) - np.mean(ref)) < 5e-3 * np.mean(ref)
+    assert abs(cnt[0] - st["extension_rays"]) <= 0.02 * st["extension_rays"]
+
+
 # ---- CLI surface (src/main.cpp:16-49) ---------------------------------------------------------------------
 CLI = os.path.join(ROOT, "bin", "raytracer_b200")
 
